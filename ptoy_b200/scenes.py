@@ -1,0 +1,166 @@
+"""Synthetic scenes of SURVEY.md §8(d) / BASELINE.json ``configs`` (numpy, host side).
+
+Every generator returns a ``Scene`` whose arrays are float32 / int32, seeded and
+deterministic, so the same state can be loaded into the CUDA engine, the CPU
+oracle and the compiled reference.  Constants follow particles.cpp:7-24.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+R = np.float32(0.02)           # kRadius, particles.cpp:7
+BLOCK = np.float32(4.0 * 0.02)  # kBlockSize as the reference rounds it (0x3da3d70a)
+assert np.float32(4.0 * float(np.float32(0.02))) == np.float32(0.08)
+
+
+@dataclass
+class Scene:
+    domain: tuple                      # (ax, ay, bx, by)
+    pos: np.ndarray                    # [n,2] f32
+    vel: np.ndarray                    # [n,2] f32
+    ids: np.ndarray                    # [n] i32
+    bonds: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.int32))  # directed, both ways
+    frozen: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    portals: list = field(default_factory=list)    # [(b0,e0,b1,e1)] xy tuples
+    gravity: tuple = (True, (0.0, -10.0))
+    name: str = ""
+
+    @property
+    def n(self):
+        return len(self.ids)
+
+
+def _box_for(n, pitch, aspect=4.0 / 3.0):
+    """Domain [-1,-1]..[bx,by] that holds ≈n hex-packed particles at `pitch`."""
+    row_h = pitch * np.sqrt(3.0) / 2.0
+    area = n * pitch * row_h
+    w = np.sqrt(area * aspect)
+    h = area / w
+    return float(w), float(h)
+
+
+def hex_lattice(n, pitch_over_r=2.2, jitter_over_r=0.025, seed=1234, aspect=4.0 / 3.0,
+                vel_scale=0.0):
+    """Jittered hexagonal packing (parity scenes C2/C3/C5 of SURVEY.md §8d).
+
+    Particles fill rows bottom-up inside the frame walls; ids follow lattice order
+    (row-major), so bonds between lattice neighbours are also id-local.
+    """
+    r = float(R)
+    pitch = pitch_over_r * r
+    w, h = _box_for(n, pitch, aspect)
+    cols = max(1, int(np.floor((w - 2 * r - pitch / 2) / pitch)))
+    rows = int(np.ceil(n / cols))
+    row_h = pitch * np.sqrt(3.0) / 2.0
+    bx = -1.0 + 2 * r + pitch * (cols + 0.5)
+    by = -1.0 + 2 * r + row_h * rows + pitch
+    k = np.arange(n, dtype=np.int64)
+    j, i = k // cols, k % cols
+    x = -1.0 + r + pitch * (i + 0.5 + 0.5 * (j % 2))
+    y = -1.0 + r + pitch * 0.5 + row_h * j
+    rng = np.random.RandomState(seed)
+    jit = (rng.uniform(-1.0, 1.0, size=(n, 2)) * (jitter_over_r * r))
+    pos = np.stack([x, y], axis=1) + jit
+    vel = np.zeros((n, 2))
+    if vel_scale:
+        vel = rng.uniform(-vel_scale, vel_scale, size=(n, 2))
+    sc = Scene((-1.0, -1.0, float(np.float32(bx)), float(np.float32(by))),
+               pos.astype(np.float32), vel.astype(np.float32),
+               np.arange(n, dtype=np.int32), name=f"hex{n}")
+    sc.lattice = (rows, cols)
+    return sc
+
+
+def uniform_random(n, seed=1234, density=596.0, aspect=4.0 / 3.0):
+    """i.i.d. uniform positions (C2 throughput scene; overlapping → single-step parity only)."""
+    area = n / density
+    w = float(np.sqrt(area * aspect))
+    h = area / w
+    r = float(R)
+    rng = np.random.RandomState(seed)
+    pos = np.empty((n, 2))
+    pos[:, 0] = rng.uniform(-1.0 + r, -1.0 + w - r, size=n)
+    pos[:, 1] = rng.uniform(-1.0 + r, -1.0 + h - r, size=n)
+    return Scene((-1.0, -1.0, float(np.float32(-1.0 + w)), float(np.float32(-1.0 + h))),
+                 pos.astype(np.float32), np.zeros((n, 2), np.float32),
+                 np.arange(n, dtype=np.int32), name=f"uniform{n}")
+
+
+def add_lattice_bonds(scene, keep_prob=2.0 / 3.0, seed=99):
+    """C3: each of the 3 forward hex-neighbour edges kept with p=2/3 → mean directed
+    degree ≈4; both directions stored (particles.cpp:493-494)."""
+    rows, cols = scene.lattice
+    n = scene.n
+    k = np.arange(n, dtype=np.int64)
+    j, i = k // cols, k % cols
+    rng = np.random.RandomState(seed)
+    edges = []
+    # forward neighbours: right; up-left/up-right depending on row parity
+    cand = [(k + 1, i + 1 < cols)]
+    up = k + cols
+    odd = (j % 2) == 1
+    # even row: up (same i) and up-left (i-1); odd row: up (same i) and up-right (i+1)
+    cand.append((up, np.ones(n, bool)))
+    diag = np.where(odd, up + 1, up - 1)
+    diag_ok = np.where(odd, i + 1 < cols, i - 1 >= 0)
+    cand.append((diag, diag_ok))
+    for nb, ok in cand:
+        ok = ok & (nb < n) & (nb >= 0)
+        keep = rng.uniform(size=n) < keep_prob
+        m = ok & keep
+        edges.append(np.stack([k[m], nb[m]], axis=1))
+    e = np.concatenate(edges, axis=0)
+    both = np.concatenate([e, e[:, ::-1]], axis=0).astype(np.int32)
+    order = np.lexsort((both[:, 1], both[:, 0]))
+    scene.bonds = np.ascontiguousarray(both[order])
+    scene.frozen = np.nonzero(rng.uniform(size=n) < 0.01)[0].astype(np.int32)
+    scene.name += "+bonds"
+    return scene
+
+
+def add_portals(scene, n_pairs, length=1.0, seed=7):
+    """C4: axis-aligned vertical portal pairs, members ≥10 units apart when the
+    domain allows it, spread over the domain width so pairs straddle strips."""
+    ax, ay, bx, by = scene.domain
+    rng = np.random.RandomState(seed)
+    w, h = bx - ax, by - ay
+    length = min(length, 0.5 * h)
+    for p in range(n_pairs):
+        x0 = ax + w * (0.05 + 0.4 * rng.uniform())
+        x1 = ax + w * (0.55 + 0.4 * rng.uniform())
+        y0 = ay + 0.1 + (h - length - 0.2) * rng.uniform()
+        y1 = ay + 0.1 + (h - length - 0.2) * rng.uniform()
+        scene.portals.append(((x0, y0), (x0, y0 + length), (x1, y1), (x1, y1 + length)))
+    scene.name += f"+{n_pairs}portals"
+    return scene
+
+
+def config3(n=16_000_000, seed=1234):
+    """BASELINE.json configs[2]: hex pitch 2.02r, jitter ±0.01r, ~4 directed bonds per
+    particle, 1 % frozen."""
+    sc = hex_lattice(n, pitch_over_r=2.02, jitter_over_r=0.01, seed=seed)
+    return add_lattice_bonds(sc)
+
+
+def config2_parity(n=1_000_000, seed=1234):
+    return hex_lattice(n, pitch_over_r=2.2, jitter_over_r=0.025, seed=seed)
+
+
+def config4(n=64_000_000, n_pairs=64, seed=1234):
+    sc = hex_lattice(n, pitch_over_r=2.2, jitter_over_r=0.025, seed=seed, vel_scale=0.5)
+    return add_portals(sc, n_pairs)
+
+
+def load_into(obj, scene):
+    """Load `scene` into anything exposing the common loader methods
+    (ptoy_b200.Particles, oracle RefParticles / PortParticles)."""
+    obj.reset_scene(scene.domain)
+    obj.set_gravity(scene.gravity[0], scene.gravity[1])
+    obj.add_particles(scene.pos, scene.vel, scene.ids)
+    for p in scene.portals:
+        obj.add_portal_pair(*p)
+    if len(scene.bonds):
+        obj.set_bonds(scene.bonds)
+    if len(scene.frozen):
+        obj.set_frozen(scene.frozen)
+    return obj

@@ -1,0 +1,43 @@
+"""In-tree build of the CUDA engine: nvcc -> ptoy_b200/libptoy_b200.so (sm_100a only)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libptoy_b200.so")
+SOURCES = ["kernels.cu", "engine.cu", "c_api.cu"]
+NVCC = os.environ.get("PTOY_NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function", "-shared",
+    "-ccbin", "/usr/bin/g++", "-cudart", "static",
+]
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(HERE, "..", "include", "ptoy_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libptoy_b200.so")
+    if verbose:
+        print(r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose="-v" in sys.argv)
+    print(LIB)

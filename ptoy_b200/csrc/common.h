@@ -1,0 +1,172 @@
+// Shared host/device definitions of the ptoy_b200 engine.
+//
+// Data layout in HBM: particles live in structure-of-arrays
+// buffers (float2 pos, float2 vel, int id) sorted by SUB-CELL key.  A sub-cell is
+// half a reference block in each direction (blocks.h: block size 4r = 0.08, so a
+// sub-cell is 2r = 0.04 = the pair cutoff); `start[key]` is the exclusive prefix
+// sum of sub-cell populations.  Reference block (i,j) = sub-rows {2i+4, 2i+5}
+// x sub-columns {2j+4, 2j+5} of the padded sub-grid (plus the low band {2,3} for
+// i==0 / j==0, which holds the particles the reference's truncating FindBlock
+// maps to row/column 0 from outside the grid, blocks.h:155-163).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ptoy {
+
+constexpr int kMaxWalls = 16;
+constexpr int kThreads = 256;
+
+// Sub-cell grid.  S = floor(2*t) + 4 with t = fl(fl(x - A)/bs) exactly as
+// blocks::FindBlock computes it (blocks.h:156-158).
+struct GridDev {
+  float Ax, Ay;    // blocks::domain_.A
+  float bsx, bsy;  // blocks::block_size_
+  int di, dj;      // blocks::dims_
+  float fdi, fdj;  // (float)dims
+  int SI, SJ;      // padded sub-grid dims: 2*d + 6
+  int ncell;       // SI*SJ ; key == ncell is the trash bin (particle left the grid)
+};
+
+// Physics constants, computed on the host with the reference's own expression
+// types (particles.cpp:7-24) so the bit patterns agree.
+struct Phys {
+  float dt;
+  float c1, c2;          // fl(dt*0.5/m), fl(dt/m)        particles.cpp:116,145
+  float gfx, gfy;        // gravity_*kMass                particles.cpp:850
+  int gravity_enable;
+  float diss;            // kDissipation*kMass            particles.cpp:880
+  float RR, thr, r2c;    // pair: fl(R*R), r^2 threshold, first r^2 with zero force
+  float radius;          // kRadius
+  float RRw;             // wall: fl(r*r)                 particles.cpp:574-578
+  float wall_reach;      // conservative |p-Q| beyond which F12wall is exactly 0
+  float RRe;             // portal edge: fl(R*R), R=3r    particles.cpp:740
+  float vlimit;          // kVelocityLimit
+  float bondR, bond_cutoff, sigma_bond;  // particles.cpp:728-729,777
+  double bond_portal_reach;              // 2.*kPortalThickness + kCutoff   :808
+  float pickR, sigma_pick;               // particles.cpp:752-753
+  float portal_thickness;
+  double two_pt;         // 2.*kPortalThickness (double)  :284,371,812
+  int force_enabled, force_attractive;
+  float fcx, fcy;
+  float point_force, point_force_attractive;
+  int pick_enabled, pick_id;
+  float pkx, pky;
+};
+
+struct WallDev {
+  float ax, ay, bx, by;          // line A,B (particles.h:35)
+  float lox, loy, hix, hiy;      // bbox grown by wall_reach: outside it the force is 0
+};
+
+// One portal (pair p, side d) = entry 2p+d; r, n, rr as every user recomputes them
+// (e.g. particles.cpp:293-296): r = end-begin, n = normalized(-r.y, r.x), rr = r.r
+struct PortalSide {
+  float ax, ay, bx, by;
+  float rx, ry, nx, ny;
+  float rr;
+  float pad[3];
+};
+
+struct Counters {
+  int n_cur;        // particles alive (valid slots [0,n_cur))
+  int n_next;       // alive after the pending reorder
+  int n_total;      // n_next + trash
+  int removed_total;
+  int max_sub_occupancy;
+  int err_flags;
+};
+
+struct StageArgs {
+  GridDev g;
+  Phys ph;
+  WallDev walls[kMaxWalls];
+  int n_walls;
+  float free_lox, free_loy, free_hix, free_hiy;  // strictly inside: no wall acts
+  const Counters* ctr;
+  const float2* pos;     // x0 (binning-time positions), sorted by sub-cell key
+  const float2* vel;     // v0
+  float2* pos_h;         // x_half
+  float2* vel_h;         // v_half
+  float2* pos_out;       // stage 2: x' (may alias pos)
+  float2* vel_out;       // stage 2: v'
+  const int* id;
+  const int* start;      // [ncell+2] exclusive prefix of sub-cell populations
+  float margin;          // extra search margin in sub-cell units
+  // frozen_ as a bitmask over ids
+  const uint32_t* frozen_bits;
+  int has_frozen;
+  // bonds_ as CSR over ids: row = .first, columns ascending = std::set order
+  const uint32_t* bond_ptr;
+  const int* bond_col;
+  const int* slot_of_id;
+  int has_bonds;
+  // portals
+  int n_sides;           // 2 * pairs
+  const PortalSide* sides;
+  const int* pblk_ptr;   // [n_sides+1] into pblk
+  const int* pblk;       // Portal::blocks, ascending
+  const uint8_t* blk_flags;  // per reference block: bit0 in a portal list, bit1 near a portal end
+  int need_id;
+  // outputs
+  float2* force_out;     // optional, by slot
+  int* newkey;           // stage 2
+  int* cnt;              // stage 2: sub-cell histogram (RED)
+  int do_tail;           // stage 2: teleport + key + histogram fused
+  int write_state;       // 0 = forces only (debug)
+};
+
+struct TailArgs {  // standalone teleport + key pass (resize iterations, add_particles)
+  GridDev g;
+  Phys ph;
+  const Counters* ctr;
+  float2* pos;
+  float2* vel;
+  int n_sides;
+  const PortalSide* sides;
+  const int* pblk_ptr;
+  const int* pblk;
+  const uint8_t* blk_flags;
+  int do_teleport;
+  int first;     // particles [first, n) are processed
+  int* newkey;
+  int* cnt;
+};
+
+struct ReorderArgs {
+  const Counters* ctr;
+  int ncell;
+  const int* newkey;
+  const int* start;
+  int* cnt;          // histogram on entry; fill counts it down to zero
+  int* order;        // order[new slot] = old slot (nondeterministic within a cell)
+  const float2* pos_in;
+  const float2* vel_in;
+  const int* id_in;
+  float2* pos_out;
+  float2* vel_out;
+  int* id_out;
+  int* slot_of_id;   // optional
+};
+
+// launchers (kernels.cu)
+void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s);
+void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s);
+void launch_scan(const int* cnt, int* start, int n_items, int ncell, unsigned long long* tile_state,
+                 int* ticket, unsigned epoch, Counters* ctr, cudaStream_t s);
+void launch_fill(const ReorderArgs& a, int n_bound, cudaStream_t s);
+void launch_gather(const ReorderArgs& a, int n_bound, cudaStream_t s);
+void launch_finalize(Counters* ctr, int* ticket, cudaStream_t s);
+void launch_find_blocks(const GridDev& g, const float2* pos, size_t n, long long* out, cudaStream_t s);
+void launch_state_by_id(const GridDev& g, const Counters* ctr, const float2* pos, const float2* vel,
+                        const int* id, int n_bound, float2* pos_by_id, float2* vel_by_id,
+                        long long* block_by_id, cudaStream_t s);
+void launch_scatter_by_id(const Counters* ctr, const float2* val, const int* id, int n_bound,
+                          float2* out_by_id, cudaStream_t s);
+void launch_block_of_slot(const GridDev& g, const Counters* ctr, const float2* pos, int n_bound,
+                          int* block, cudaStream_t s);
+void launch_slot_map(const Counters* ctr, const int* id, int n_bound, int* slot_of_id, cudaStream_t s);
+void launch_fill_i32(int* p, int v, size_t n, cudaStream_t s);
+int scan_tile_items();
+
+}  // namespace ptoy

@@ -1,0 +1,713 @@
+// Hand-written sm_100a kernels of the particle-stepping hot path.
+//
+// Arithmetic contract: every floating-point operation that the reference performs
+// (scalar build, no FMA) is issued here as the same single IEEE
+// binary32 operation through the __f*_rn intrinsics, which nvcc never contracts
+// into FMAs.  A pair/wall/bond/portal contribution is therefore bit-identical to
+// the reference's; only the ORDER in which a particle's pair contributions are
+// summed differs (sub-cell order instead of block/slot order).
+//
+// Kernels (one launch each per iteration):
+//   stage_kernel<1>  forces at x0 + half kick/drift          particles.cpp:97-123
+//   stage_kernel<2>  forces at x_half + full update + portal teleport + new
+//                    sub-cell key + histogram                particles.cpp:128-153,177-179
+//   scan_kernel      single-pass decoupled look-back exclusive scan of the histogram
+//   fill_kernel      counting-sort slot assignment
+//   gather_kernel    deterministic (stable) reorder of pos/vel/id + id->slot map
+#include "common.h"
+
+namespace ptoy {
+
+// ---------------------------------------------------------------------------------
+// exact-rounding float helpers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// (float)(1. / (double)x): double division then rounding to float equals the
+// correctly rounded float quotient (53 >= 2*24+2), i.e. __fdiv_rn(1, x).
+__device__ __forceinline__ float rcp_exact(float x) { return __fdiv_rn(1.0f, x); }
+// geometry.h:62-64  dot = v.x*x + v.y*y
+__device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) {
+  return fadd(fmul(ax, bx), fmul(ay, by));
+}
+// geometry.h:65-67  length = sqrt(x*x + y*y) (double sqrt of a float, rounded back:
+// identical to the correctly rounded float sqrt)
+__device__ __forceinline__ float len2(float x, float y) { return __fsqrt_rn(dot2(x, y, x, y)); }
+// std::max<float>(0, k) = (0 < k) ? k : 0   (NaN -> 0)
+__device__ __forceinline__ float max0(float k) { return (0.0f < k) ? k : 0.0f; }
+
+// ---------------------------------------------------------------------------------
+// binning (blocks::FindBlock, blocks.h:155-163) at sub-cell resolution
+// ---------------------------------------------------------------------------------
+struct Cell {
+  int Si, Sj;     // padded sub-cell row / column
+  float ui, uj;   // fractional position inside the sub-cell, [0,1)
+  bool valid;     // FindBlock != kBlockNone
+};
+
+__device__ __forceinline__ Cell cell_of(const GridDev& g, float2 p) {
+  Cell c;
+  const float tx = fdiv(fsub(p.x, g.Ax), g.bsx);
+  const float ty = fdiv(fsub(p.y, g.Ay), g.bsy);
+  // (int)t truncates toward zero: t in (-1,0) still maps to row/column 0
+  c.valid = (tx > -1.0f) && (tx < g.fdi) && (ty > -1.0f) && (ty < g.fdj);
+  const float wx = tx * 2.0f, wy = ty * 2.0f;  // exact
+  const float fx = floorf(wx), fy = floorf(wy);
+  c.Si = (int)fx + 4;
+  c.Sj = (int)fy + 4;
+  c.ui = wx - fx;  // exact
+  c.uj = wy - fy;
+  return c;
+}
+__device__ __forceinline__ int block_of(const GridDev& g, const Cell& c) {
+  const int bi = max(0, (c.Si - 4) >> 1), bj = max(0, (c.Sj - 4) >> 1);
+  return bi * g.dj + bj;
+}
+// sub-rows / sub-columns (inclusive) that make up reference block `blk`
+__device__ __forceinline__ void block_extent(const GridDev& g, int blk, int& r0, int& r1, int& c0, int& c1) {
+  const int bi = blk / g.dj, bj = blk - bi * g.dj;
+  r0 = (bi == 0) ? 2 : 2 * bi + 4;
+  r1 = 2 * bi + 5;
+  c0 = (bj == 0) ? 2 : 2 * bj + 4;
+  c1 = 2 * bj + 5;
+}
+
+// ---------------------------------------------------------------------------------
+// force laws
+// ---------------------------------------------------------------------------------
+// particles.cpp:584-595 F12 for a pair already known to be inside the cutoff
+// (r2 < r2c <=> the clamped coefficient is > 0, see engine.cu find_r2c()).
+__device__ __forceinline__ void pair_force(const Phys& ph, float dx, float dy, float r2, float& fx, float& fy) {
+  const float r2t = (ph.thr < r2) ? r2 : ph.thr;  // std::max(threshold, r2)
+  const float inv = rcp_exact(r2t);
+  const float d2 = fmul(inv, ph.RR);
+  const float d6 = fmul(fmul(d2, d2), d2);
+  const float d12 = fmul(d6, d6);
+  const float k = fmul(fsub(d12, d6), inv);  // sigma = 1
+  fx = fmul(dx, k);
+  fy = fmul(dy, k);
+}
+// particles.cpp:572-582 / :738-749: no threshold, clamp by std::max<Scal>(0., .)
+__device__ __forceinline__ void lj_noclamp(float RR, float px, float py, float qx, float qy, float& fx, float& fy) {
+  const float dx = fsub(px, qx), dy = fsub(py, qy);
+  const float r2 = dot2(dx, dy, dx, dy);
+  const float inv = rcp_exact(r2);
+  const float d2 = fmul(inv, RR);
+  const float d6 = fmul(fmul(d2, d2), d2);
+  const float d12 = fmul(d6, d6);
+  const float k = max0(fmul(fsub(d12, d6), inv));
+  fx = fmul(dx, k);
+  fy = fmul(dy, k);
+}
+// particles.cpp:727-736 F12_bond
+__device__ __forceinline__ void bond_force(const Phys& ph, float px, float py, float qx, float qy, float& fx, float& fy) {
+  const float dx = fsub(px, qx), dy = fsub(py, qy);
+  const float r = len2(dx, dy);
+  // k = max(1. - r/R, 1. - 5) in double, rounded to float.  1 - x is exact in
+  // double for float x >= 2^-29 and rounds to 1.0f either way below that, so
+  // the float subtraction gives the same float; -4 is exact.
+  const float q = fdiv(r, ph.bondR);
+  float k = fsub(1.0f, q);
+  k = (k < -4.0f) ? -4.0f : k;  // std::max(a, b) = (a < b) ? b : a
+  const float s = fmul(ph.sigma_bond, k);
+  fx = fmul(dx, s);
+  fy = fmul(dy, s);
+}
+
+// particles.h:37-46 line::GetNearest
+__device__ __forceinline__ void seg_nearest(float ax, float ay, float bx, float by, float px, float py, float& qx, float& qy) {
+  const float abx = fsub(bx, ax), aby = fsub(by, ay);
+  const float apx = fsub(px, ax), apy = fsub(py, ay);
+  const float lambda = fdiv(dot2(abx, aby, apx, apy), dot2(abx, aby, abx, aby));
+  if (lambda > 0.0f && lambda < 1.0f) {
+    qx = fadd(ax, fmul(abx, lambda));
+    qy = fadd(ay, fmul(aby, lambda));
+  } else {
+    const float da = len2(fsub(ax, px), fsub(ay, py));  // p.dist(A) = (A - p).length()
+    const float db = len2(fsub(bx, px), fsub(by, py));
+    if (da < db) { qx = ax; qy = ay; } else { qx = bx; qy = by; }
+  }
+}
+
+// lambda / offset of point p in the frame of a portal (e.g. particles.cpp:340-341)
+__device__ __forceinline__ void portal_coords(const PortalSide& s, float px, float py, float& lambda, float& offset) {
+  const float dx = fsub(px, s.ax), dy = fsub(py, s.ay);
+  lambda = fdiv(dot2(s.rx, s.ry, dx, dy), s.rr);
+  offset = dot2(dx, dy, s.nx, s.ny);
+}
+// a + r*lambda + n*(offset + 2.*sign*thickness)   (particles.cpp:369-371, 810-812)
+__device__ __forceinline__ void portal_image(const Phys& ph, const PortalSide& s, float lambda_q, float offset_q, float sign, float& x, float& y) {
+  const float shifted = __double2float_rn(__dadd_rn((double)offset_q, __dmul_rn(__dmul_rn(2.0, (double)sign), (double)ph.portal_thickness)));
+  x = fadd(fadd(s.ax, fmul(s.rx, lambda_q)), fmul(s.nx, shifted));
+  y = fadd(fadd(s.ay, fmul(s.ry, lambda_q)), fmul(s.ny, shifted));
+}
+
+__device__ __forceinline__ bool in_sorted(const int* __restrict__ list, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (list[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && list[lo] == v;
+}
+
+// ---------------------------------------------------------------------------------
+// all forces on one particle (particles.cpp:839-910 calc_forces, :761-826 RHS_bonds,
+// :318-381 ApplyPortalsForces), summed in the reference's order of force kinds
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float2 particle_force(
+    const StageArgs& a, const float2* __restrict__ X, int slot, int pid, float2 x, float2 v,
+    const Cell& c, int blk, unsigned flags) {
+  const Phys& ph = a.ph;
+  float fx = 0.0f, fy = 0.0f;
+  if (ph.gravity_enable) { fx = ph.gfx; fy = ph.gfy; }                       // :849-851
+
+  if (ph.force_enabled) {                                                    // :854-863
+    const float rx = fsub(x.x, ph.fcx), ry = fsub(x.y, ph.fcy);
+    const float l = len2(rx, ry);
+    if (l > ph.radius) {
+      const double ld = (double)l;
+      float s;
+      if (ph.force_attractive) {
+        const double l3 = __dmul_rn(__dmul_rn(ld, ld), ld);                  // pow(l, 3)
+        s = __double2float_rn(__ddiv_rn((double)(-ph.point_force_attractive), l3));
+      } else {
+        const double l2 = __dmul_rn(ld, ld);
+        s = __double2float_rn(__ddiv_rn((double)ph.point_force, __dmul_rn(l2, l2)));  // pow(l, 4)
+      }
+      fx = fadd(fx, fmul(rx, s));
+      fy = fadd(fy, fmul(ry, s));
+    }
+  }
+
+  if (flags & 2u) {                                                          // :866-871
+    for (int s = 0; s < a.n_sides; ++s) {
+      const PortalSide ps = a.sides[s];
+      float ex, ey;
+      lj_noclamp(ph.RRe, x.x, x.y, ps.ax, ps.ay, ex, ey);
+      fx = fadd(fx, ex); fy = fadd(fy, ey);
+      lj_noclamp(ph.RRe, x.x, x.y, ps.bx, ps.by, ex, ey);
+      fx = fadd(fx, ex); fy = fadd(fy, ey);
+    }
+  }
+
+  if (ph.pick_enabled && pid == ph.pick_id) {                                // :874-876, :751-759
+    const float dx = fsub(x.x, ph.pkx), dy = fsub(x.y, ph.pky);
+    const float r = len2(dx, dy);
+    const float k = fdiv(fsub(ph.pickR, r), ph.pickR);
+    const float s = fmul(ph.sigma_pick, k);
+    fx = fadd(fx, fmul(dx, s));
+    fy = fadd(fy, fmul(dy, s));
+  }
+
+  fx = fsub(fx, fmul(v.x, ph.diss));                                         // :880
+  fy = fsub(fy, fmul(v.y, ph.diss));
+
+  // ---- pair loop (:884-900 + :598-606) over the sub-cell neighbourhood ----------
+  {
+    const int r_lo = c.Si - 1 - (c.ui < a.margin), r_hi = c.Si + 1 + (c.ui > 1.0f - a.margin);
+    const int c_lo = c.Sj - 1 - (c.uj < a.margin), c_hi = c.Sj + 1 + (c.uj > 1.0f - a.margin);
+    for (int R = r_lo; R <= r_hi; ++R) {
+      const int base = R * a.g.SJ;
+      const int beg = __ldg(a.start + base + c_lo), end = __ldg(a.start + base + c_hi + 1);
+      for (int q = beg; q < end; ++q) {
+        const float2 pq = X[q];
+        const float dx = fsub(x.x, pq.x), dy = fsub(x.y, pq.y);
+        const float r2 = dot2(dx, dy, dx, dy);
+        if (r2 < ph.r2c && q != slot) {
+          float px, py;
+          pair_force(ph, dx, dy, r2, px, py);
+          fx = fadd(fx, px);
+          fy = fadd(fy, py);
+        }
+      }
+    }
+  }
+
+  // ---- walls (:903-909); exact zero outside each wall's grown bbox ----------------
+  if (!(x.x > a.free_lox && x.x < a.free_hix && x.y > a.free_loy && x.y < a.free_hiy)) {
+    for (int k = 0; k < a.n_walls; ++k) {
+      const WallDev w = a.walls[k];
+      if (x.x >= w.lox && x.x <= w.hix && x.y >= w.loy && x.y <= w.hiy) {
+        float qx, qy, wx, wy;
+        seg_nearest(w.ax, w.ay, w.bx, w.by, x.x, x.y, qx, qy);
+        lj_noclamp(ph.RRw, x.x, x.y, qx, qy, wx, wy);
+        fx = fadd(fx, wx);
+        fy = fadd(fy, wy);
+      }
+    }
+  }
+
+  // ---- bonds (:761-826), CSR row of this id, partners ascending ------------------
+  if (a.has_bonds) {
+    const unsigned e0 = a.bond_ptr[pid], e1 = a.bond_ptr[pid + 1];
+    for (unsigned e = e0; e < e1; ++e) {
+      const int sb = a.slot_of_id[a.bond_col[e]];
+      if (sb < 0) continue;  // partner left the grid: bond erased by CheckBonds (:205-215)
+      const float2 q = X[sb];
+      float bx, by;
+      const float dist = len2(fsub(q.x, x.x), fsub(q.y, x.y));               // p_pos.dist(q_pos)
+      bool found = false;
+      if (!(dist < ph.bond_cutoff)) {                                        // :784-819
+        for (int s = 0; s < a.n_sides; ++s) {
+          const PortalSide po = a.sides[s];
+          const PortalSide ot = a.sides[s ^ 1];
+          float p_lambda, p_offset, q_lambda, q_offset;
+          portal_coords(po, x.x, x.y, p_lambda, p_offset);
+          portal_coords(ot, q.x, q.y, q_lambda, q_offset);
+          if (p_lambda > 0.0f && p_lambda < 1.0f && q_lambda > 0.0f && q_lambda < 1.0f &&
+              fmul(p_offset, q_offset) < 0.0f &&
+              (double)fabsf(fsub(p_offset, q_offset)) < ph.bond_portal_reach) {
+            const float sign = (p_offset > 0.0f) ? 1.0f : -1.0f;
+            float jx, jy;
+            portal_image(ph, po, q_lambda, q_offset, sign, jx, jy);
+            bond_force(ph, x.x, x.y, jx, jy, bx, by);
+            found = true;  // no break: the last matching (pair, side) wins
+          }
+        }
+      }
+      if (!found) bond_force(ph, x.x, x.y, q.x, q.y, bx, by);
+      fx = fadd(fx, bx);
+      fy = fadd(fy, by);
+    }
+  }
+
+  // ---- cross-portal forces (:318-381) ------------------------------------------------
+  if (flags & 1u) {
+    for (int s = 0; s < a.n_sides; ++s) {
+      const int lb = a.pblk_ptr[s], le = a.pblk_ptr[s + 1];
+      if (!in_sorted(a.pblk + lb, le - lb, blk)) continue;
+      const PortalSide po = a.sides[s];
+      const PortalSide ot = a.sides[s ^ 1];
+      float lambda_c, offset_c;
+      portal_coords(po, x.x, x.y, lambda_c, offset_c);
+      if (!(lambda_c > 0.0f && lambda_c < 1.0f)) continue;
+      // same-portal particles on the other side of the plane: subtract (:345-355)
+      for (int l = lb; l < le; ++l) {
+        int r0, r1, c0, c1;
+        block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
+        for (int R = r0; R <= r1; ++R) {
+          const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
+          for (int q = beg; q < end; ++q) {
+            const float2 nb = X[q];
+            float ln, on;
+            portal_coords(po, nb.x, nb.y, ln, on);
+            if (ln > 0.0f && ln < 1.0f && fmul(on, offset_c) < 0.0f) {
+              const float dx = fsub(x.x, nb.x), dy = fsub(x.y, nb.y);
+              const float r2 = dot2(dx, dy, dx, dy);
+              if (r2 < ph.r2c) {
+                float px, py;
+                pair_force(ph, dx, dy, r2, px, py);
+                fx = fsub(fx, px);
+                fy = fsub(fy, py);
+              }
+            }
+          }
+        }
+      }
+      // images of the partner portal's particles: add (:358-375)
+      const int ob = a.pblk_ptr[s ^ 1], oe = a.pblk_ptr[(s ^ 1) + 1];
+      const float sign = (offset_c > 0.0f) ? 1.0f : -1.0f;
+      for (int l = ob; l < oe; ++l) {
+        int r0, r1, c0, c1;
+        block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
+        for (int R = r0; R <= r1; ++R) {
+          const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
+          for (int q = beg; q < end; ++q) {
+            const float2 nb = X[q];
+            float oln, oon;
+            portal_coords(ot, nb.x, nb.y, oln, oon);
+            if (oln > 0.0f && oln < 1.0f && fmul(oon, offset_c) < 0.0f) {
+              float jx, jy;
+              portal_image(ph, po, oln, oon, sign, jx, jy);
+              const float dx = fsub(x.x, jx), dy = fsub(x.y, jy);
+              const float r2 = dot2(dx, dy, dx, dy);
+              if (r2 < ph.r2c) {
+                float px, py;
+                pair_force(ph, dx, dy, r2, px, py);
+                fx = fadd(fx, px);
+                fy = fadd(fy, py);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  return make_float2(fx, fy);
+}
+
+// particles.cpp:117-120: if (|v| > limit) v *= limit / |v|
+__device__ __forceinline__ void clamp_velocity(const Phys& ph, float& vx, float& vy) {
+  const float l = len2(vx, vy);
+  if (l > ph.vlimit) {
+    const float s = fdiv(ph.vlimit, l);
+    vx = fmul(vx, s);
+    vy = fmul(vy, s);
+  }
+}
+
+// DetectPortals + ApplyPortals (particles.cpp:288-316, 382-409) for one particle whose
+// reference block is `blk`, then the new sub-cell key and the histogram update
+// (the device half of blocks::SortParticles, blocks.h:215-244).
+template <class A>
+__device__ __forceinline__ void teleport(const A& a, int blk, float2& x, float2& v) {
+  bool flagged = false;
+  for (int s = 0; s < a.n_sides; ++s) {
+    const int lb = a.pblk_ptr[s], le = a.pblk_ptr[s + 1];
+    if (!in_sorted(a.pblk + lb, le - lb, blk)) continue;
+    float lambda, offset;
+    portal_coords(a.sides[s], x.x, x.y, lambda, offset);
+    if (lambda > 0.0f && lambda < 1.0f && fabsf(offset) <= a.ph.portal_thickness) flagged = true;
+  }
+  if (!flagged) return;
+  for (int s = 0; s < a.n_sides; ++s) {  // first (pair, side) whose block list holds the particle
+    const int lb = a.pblk_ptr[s], le = a.pblk_ptr[s + 1];
+    if (!in_sorted(a.pblk + lb, le - lb, blk)) continue;
+    const PortalSide src = a.sides[s];
+    const PortalSide dst = a.sides[s ^ 1];
+    // MoveToPortal (particles.cpp:264-286)
+    float lambda_pos, offset_pos;
+    portal_coords(src, x.x, x.y, lambda_pos, offset_pos);
+    // offset_pos there is src_n.dot(position - src_a): same products, same sum
+    const float lambda_vel = fdiv(dot2(src.rx, src.ry, v.x, v.y), src.rr);
+    const float offset_vel = dot2(src.nx, src.ny, v.x, v.y);
+    const float sign = (offset_pos > 0.0f) ? 1.0f : -1.0f;
+    const float shifted = __double2float_rn(
+        __dsub_rn((double)offset_pos, __dmul_rn(__dmul_rn((double)sign, 2.0), (double)a.ph.portal_thickness)));
+    x.x = fadd(fadd(dst.ax, fmul(dst.rx, lambda_pos)), fmul(dst.nx, shifted));
+    x.y = fadd(fadd(dst.ay, fmul(dst.ry, lambda_pos)), fmul(dst.ny, shifted));
+    const float vx = fadd(fmul(dst.rx, lambda_vel), fmul(dst.nx, offset_vel));
+    const float vy = fadd(fmul(dst.ry, lambda_vel), fmul(dst.ny, offset_vel));
+    v.x = vx;
+    v.y = vy;
+    return;
+  }
+}
+
+__device__ __forceinline__ void key_and_count(const GridDev& g, float2 x, int slot, int* newkey, int* cnt) {
+  const Cell nc = cell_of(g, x);
+  const int key = nc.valid ? nc.Si * g.SJ + nc.Sj : g.ncell;
+  newkey[slot] = key;
+  atomicAdd(cnt + key, 1);  // result unused -> RED.ADD
+}
+
+template <int STAGE>
+__global__ void __launch_bounds__(kThreads) stage_kernel(const __grid_constant__ StageArgs a) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= a.ctr->n_cur) return;
+  const float2 x0 = a.pos[i];
+  float2 v0 = a.vel[i];
+  float2 x, v;
+  if (STAGE == 1) { x = x0; v = v0; } else { x = a.pos_h[i]; v = a.vel_h[i]; }
+  const float2* __restrict__ X = (STAGE == 1) ? a.pos : (const float2*)a.pos_h;
+  const Cell c = cell_of(a.g, x0);
+  const int blk = block_of(a.g, c);
+  const unsigned flags = a.blk_flags ? a.blk_flags[blk] : 0u;
+  const int pid = a.need_id ? a.id[i] : 0;
+
+  float2 f = particle_force(a, X, i, pid, x, v, c, blk, flags);
+
+  bool frozen = false;
+  if (a.has_frozen) frozen = (a.frozen_bits[pid >> 5] >> (pid & 31)) & 1u;
+  if (frozen) {                                                      // particles.cpp:828-837
+    v.x = fmul(v.x, 0.0f); v.y = fmul(v.y, 0.0f);
+    f.x = fmul(f.x, 0.0f); f.y = fmul(f.y, 0.0f);
+    v0.x = fmul(v0.x, 0.0f); v0.y = fmul(v0.y, 0.0f);  // velocity_tmp was saved after ApplyFrozen
+  }
+  if (a.force_out) a.force_out[i] = f;
+  if (!a.write_state) return;
+
+  const Phys& ph = a.ph;
+  if (STAGE == 1) {                                                  // particles.cpp:109-123
+    float vx = fadd(v.x, fmul(f.x, ph.c1));
+    float vy = fadd(v.y, fmul(f.y, ph.c1));
+    clamp_velocity(ph, vx, vy);
+    const float xh = fadd(x.x, fmul(fmul(vx, ph.dt), 0.5f));
+    const float yh = fadd(x.y, fmul(fmul(vy, ph.dt), 0.5f));
+    a.pos_h[i] = make_float2(xh, yh);
+    a.vel_h[i] = make_float2(vx, vy);
+  } else {                                                           // particles.cpp:140-153
+    float vx = fadd(v0.x, fmul(f.x, ph.c2));
+    float vy = fadd(v0.y, fmul(f.y, ph.c2));
+    clamp_velocity(ph, vx, vy);
+    float2 xn = make_float2(fadd(x0.x, fmul(vx, ph.dt)), fadd(x0.y, fmul(vy, ph.dt)));
+    float2 vn = make_float2(vx, vy);
+    if (a.do_tail) {
+      if (flags & 1u) teleport(a, blk, xn, vn);
+      key_and_count(a.g, xn, i, a.newkey, a.cnt);
+    }
+    a.pos_out[i] = xn;
+    a.vel_out[i] = vn;
+  }
+}
+
+// Standalone teleport + key pass: used when the block grid changed between the
+// update and DetectPortals (particles.cpp:157-179) and for add_particles.
+__global__ void __launch_bounds__(kThreads) tail_kernel(const __grid_constant__ TailArgs a) {
+  const int i = a.first + blockIdx.x * kThreads + threadIdx.x;
+  if (i >= a.ctr->n_cur) return;
+  float2 x = a.pos[i];
+  if (a.do_teleport && a.n_sides) {
+    const Cell c = cell_of(a.g, x);
+    const int blk = block_of(a.g, c);
+    if (c.valid && (a.blk_flags[blk] & 1u)) {
+      float2 v = a.vel[i];
+      teleport(a, blk, x, v);
+      a.pos[i] = x;
+      a.vel[i] = v;
+    }
+  }
+  key_and_count(a.g, x, i, a.newkey, a.cnt);
+}
+
+// ---------------------------------------------------------------------------------
+// single-pass exclusive scan (decoupled look-back), 1024 ints per tile
+// ---------------------------------------------------------------------------------
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kThreads * kScanItems;
+int scan_tile_items() { return kScanTile; }
+
+__global__ void __launch_bounds__(kThreads) scan_kernel(
+    const int* __restrict__ cnt, int* __restrict__ start, int n_items, int ncell,
+    unsigned long long* tile_state, int* ticket, unsigned epoch, Counters* ctr) {
+  __shared__ int s_tile;
+  __shared__ int s_warp[kThreads / 32];
+  __shared__ int s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int base = tile * kScanTile + threadIdx.x * kScanItems;
+  int4 v = make_int4(0, 0, 0, 0);
+  if (base < n_items) {  // n_items is padded to a multiple of 4
+    v = *reinterpret_cast<const int4*>(cnt + base);
+  }
+  const int tsum = v.x + v.y + v.z + v.w;
+  int incl = tsum;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = (lane < kThreads / 32) ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < kThreads / 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane < kThreads / 32) s_warp[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  const int block_total = s_warp[kThreads / 32 - 1];
+  const int excl_in_block = incl - tsum + (warp ? s_warp[warp - 1] : 0);
+
+  // publish aggregate / look back.  state = (epoch*4 + flag) << 32 | value
+  const unsigned long long tag = (unsigned long long)epoch << 2;
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* st = tile_state;
+    if (tile == 0) {
+      st[0] = ((tag | 2ull) << 32) | (unsigned)block_total;
+      s_prefix = 0;
+    } else {
+      st[tile] = ((tag | 1ull) << 32) | (unsigned)block_total;
+      int prefix = 0;
+      int t = tile - 1;
+      while (true) {
+        const unsigned long long s = st[t];
+        const unsigned long long f = s >> 32;
+        if (f == (tag | 2ull)) { prefix += (int)(unsigned)s; break; }
+        if (f == (tag | 1ull)) { prefix += (int)(unsigned)s; --t; continue; }
+        // not published yet: spin
+      }
+      st[tile] = ((tag | 2ull) << 32) | (unsigned)(prefix + block_total);
+      s_prefix = prefix;
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const int e0 = s_prefix + excl_in_block;
+  if (base < n_items) {
+    const int4 o = make_int4(e0, e0 + v.x, e0 + v.x + v.y, e0 + v.x + v.y + v.z);
+    *reinterpret_cast<int4*>(start + base) = o;
+    // totals: start[ncell] = alive, start[ncell+1] = alive + trash
+    const int o_arr[5] = {o.x, o.y, o.z, o.w, e0 + tsum};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (base + k == ncell) { ctr->n_next = o_arr[k]; ctr->n_total = o_arr[k + 1]; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// counting-sort fill + deterministic gather
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) fill_kernel(const __grid_constant__ ReorderArgs a) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= a.ctr->n_cur) return;
+  const int key = a.newkey[i];
+  // counting down leaves the histogram all-zero again for the next iteration
+  const int r = atomicSub(a.cnt + key, 1) - 1;
+  a.order[a.start[key] + r] = i;
+}
+
+// New slot k receives the particle with the (k - start[c])-th smallest OLD slot among
+// the particles of its sub-cell c: the result is the stable sort by key, independent of
+// the order in which fill_kernel's atomics were served.
+__global__ void __launch_bounds__(kThreads) gather_kernel(const __grid_constant__ ReorderArgs a) {
+  const int k = blockIdx.x * kThreads + threadIdx.x;
+  if (k >= a.ctr->n_total) return;
+  int src = a.order[k];
+  if (k >= a.ctr->n_next) {  // left the grid: removed (blocks.h:230-232)
+    if (a.slot_of_id) a.slot_of_id[a.id_in[src]] = -1;
+    return;
+  }
+  const int c = a.newkey[src];
+  const int beg = a.start[c], end = a.start[c + 1];
+  if (end - beg > 1) {
+    const int want = k - beg;
+    for (int e = beg; e < end; ++e) {
+      const int cand = a.order[e];
+      int smaller = 0;
+      for (int e2 = beg; e2 < end; ++e2) smaller += (a.order[e2] < cand);
+      if (smaller == want) { src = cand; break; }
+    }
+  }
+  a.pos_out[k] = a.pos_in[src];
+  a.vel_out[k] = a.vel_in[src];
+  const int pid = a.id_in[src];
+  a.id_out[k] = pid;
+  if (a.slot_of_id) a.slot_of_id[pid] = k;
+}
+
+__global__ void finalize_kernel(Counters* ctr, int* ticket) {
+  ctr->removed_total += ctr->n_total - ctr->n_next;
+  ctr->n_cur = ctr->n_next;
+  *ticket = 0;
+}
+
+// ---------------------------------------------------------------------------------
+// read-back helpers
+// ---------------------------------------------------------------------------------
+__global__ void find_blocks_kernel(GridDev g, const float2* pos, size_t n, long long* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Cell c = cell_of(g, pos[i]);
+  out[i] = c.valid ? (long long)block_of(g, c) : -1ll;
+}
+
+__global__ void state_by_id_kernel(GridDev g, const Counters* ctr, const float2* pos, const float2* vel,
+                                   const int* id, float2* pos_by_id, float2* vel_by_id, long long* block_by_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ctr->n_cur) return;
+  const int pid = id[i];
+  const float2 x = pos[i];
+  if (pos_by_id) pos_by_id[pid] = x;
+  if (vel_by_id) vel_by_id[pid] = vel[i];
+  if (block_by_id) {
+    const Cell c = cell_of(g, x);
+    block_by_id[pid] = c.valid ? (long long)block_of(g, c) : -1ll;
+  }
+}
+
+__global__ void scatter_by_id_kernel(const Counters* ctr, const float2* val, const int* id, float2* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ctr->n_cur) return;
+  out[id[i]] = val[i];
+}
+
+__global__ void block_of_slot_kernel(GridDev g, const Counters* ctr, const float2* pos, int* block) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ctr->n_cur) return;
+  const Cell c = cell_of(g, pos[i]);
+  block[i] = c.valid ? block_of(g, c) : -1;
+}
+
+__global__ void slot_map_kernel(const Counters* ctr, const int* id, int* slot_of_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ctr->n_cur) return;
+  slot_of_id[id[i]] = i;
+}
+
+__global__ void max_id_kernel(const int* id, size_t n, int* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int v = (i < n) ? id[i] : id[0];
+  const int mx = __reduce_max_sync(0xffffffffu, v);
+  const int mn = __reduce_min_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) { atomicMax(out, mx); atomicMin(out + 1, mn); }
+}
+
+__global__ void fill_i32_kernel(int* p, int v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s) {
+  if (n_bound <= 0) return;
+  if (stage == 1) stage_kernel<1><<<grid_for(n_bound), kThreads, 0, s>>>(a);
+  else stage_kernel<2><<<grid_for(n_bound), kThreads, 0, s>>>(a);
+}
+void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s) {
+  if (n_bound - a.first <= 0) return;
+  tail_kernel<<<grid_for(n_bound - a.first), kThreads, 0, s>>>(a);
+}
+void launch_scan(const int* cnt, int* start, int n_items, int ncell, unsigned long long* tile_state,
+                 int* ticket, unsigned epoch, Counters* ctr, cudaStream_t s) {
+  const int tiles = (n_items + kScanTile - 1) / kScanTile;
+  scan_kernel<<<tiles, kThreads, 0, s>>>(cnt, start, n_items, ncell, tile_state, ticket, epoch, ctr);
+}
+void launch_fill(const ReorderArgs& a, int n_bound, cudaStream_t s) {
+  if (n_bound <= 0) return;
+  fill_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(a);
+}
+void launch_gather(const ReorderArgs& a, int n_bound, cudaStream_t s) {
+  if (n_bound <= 0) return;
+  gather_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(a);
+}
+void launch_finalize(Counters* ctr, int* ticket, cudaStream_t s) {
+  finalize_kernel<<<1, 1, 0, s>>>(ctr, ticket);
+}
+void launch_find_blocks(const GridDev& g, const float2* pos, size_t n, long long* out, cudaStream_t s) {
+  if (!n) return;
+  find_blocks_kernel<<<grid_for(n), kThreads, 0, s>>>(g, pos, n, out);
+}
+void launch_state_by_id(const GridDev& g, const Counters* ctr, const float2* pos, const float2* vel,
+                        const int* id, int n_bound, float2* pos_by_id, float2* vel_by_id,
+                        long long* block_by_id, cudaStream_t s) {
+  if (n_bound <= 0) return;
+  state_by_id_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(g, ctr, pos, vel, id, pos_by_id, vel_by_id, block_by_id);
+}
+void launch_scatter_by_id(const Counters* ctr, const float2* val, const int* id, int n_bound,
+                          float2* out_by_id, cudaStream_t s) {
+  if (n_bound <= 0) return;
+  scatter_by_id_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(ctr, val, id, out_by_id);
+}
+void launch_block_of_slot(const GridDev& g, const Counters* ctr, const float2* pos, int n_bound,
+                          int* block, cudaStream_t s) {
+  if (n_bound <= 0) return;
+  block_of_slot_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(g, ctr, pos, block);
+}
+void launch_slot_map(const Counters* ctr, const int* id, int n_bound, int* slot_of_id, cudaStream_t s) {
+  if (n_bound <= 0) return;
+  slot_map_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(ctr, id, slot_of_id);
+}
+void launch_max_id(const int* id, size_t n, int* out, cudaStream_t s) {
+  if (!n) return;
+  max_id_kernel<<<grid_for(n), kThreads, 0, s>>>(id, n, out);
+}
+void launch_fill_i32(int* p, int v, size_t n, cudaStream_t s) {
+  if (!n) return;
+  fill_i32_kernel<<<grid_for(n), kThreads, 0, s>>>(p, v, n);
+}
+
+}  // namespace ptoy

@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the particle-stepping hot path (BASELINE.json metric: particle-updates/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n PARTICLES]
+
+One "step" = one iteration of the loop at particles.cpp:96-201 (two force evaluations + one
+re-binning) over the whole scene.  Workload at N=1: BASELINE.json configs[2] — 16M particles,
+hex packing at pitch 2.02r, ~4 directed bonds per particle, 1 % frozen.  For N>1 every rank
+owns a strip-shaped scene of the same size (weak scaling).
+
+Prints ONE JSON line (rank 0).  Keys beyond the driver's contract:
+  roofline      dominant kernel: algorithmic bytes per launch / CUDA-event duration vs the
+                measured HBM copy bandwidth (MEASURED_PEAKS.json), plus the whole-step figure
+  cpu_baseline  the reference's own CPU step (oracle/_ref, OpenMP, all host cores) on a
+                bounded sample of the same workload, timed in this run (N=1, rank 0)
+  e2e           the same metric through the C ABI with HOST buffers: per step the full state
+                is uploaded from pinned memory, stepped, and downloaded again
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PAIR = {"stage1": 32, "stage2": 48, "reorder": 40}
+METRIC = "particle-updates/sec"
+
+
+def bytes_per_update(d):
+    """Algorithmic bytes per particle-update with mean directed bond degree d."""
+    per_stage_bonds = (12 + 4 * d) if d > 0 else 0
+    k = {"stage1": 32 + per_stage_bonds, "stage2": 48 + per_stage_bonds,
+         "reorder": 40 + (4 if d > 0 else 0)}
+    k["total"] = k["stage1"] + k["stage2"] + k["reorder"]
+    return k
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def strip_scene(n, rank, world):
+    """Rank-local scene: config3 geometry, ids offset so they are globally unique."""
+    from ptoy_b200 import scenes
+    sc = scenes.config3(n, seed=1234 + rank)
+    return sc
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU Particles::step on the box's host cores."""
+    from oracle import port, ref
+    from ptoy_b200 import scenes
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_n
+    variants = [v for v in ("omp", "avx_omp") if ref.available(v)]
+    sc = scenes.config3(n)
+    best = None
+    for v in variants or ["port"]:
+        o = ref.RefParticles(v) if v != "port" else port.PortParticles()
+        scenes.load_into(o, sc)
+        for _ in range(args.warmup_ref):
+            o.step_n(1)
+        t0 = time.perf_counter()
+        o.step_n(args.steps_ref)
+        dt = time.perf_counter() - t0
+        rate = n * args.steps_ref / dt
+        if best is None or rate > best[0]:
+            best = (rate, v, o.openmp_threads, dt / args.steps_ref)
+        o.close()
+    rate, v, threads, spstep = best
+    kind = "port" if v == "port" else "reference"
+    sample = (f"configs[2] generator at n={n} (pitch 2.02r hex, ~4 bonds/particle, 1% frozen), "
+              f"{args.steps_ref} iterations after {args.warmup_ref} warm-up, build={v}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "particle-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref,
+        "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: 16M particles, ~4 bonds/particle, 1% frozen (bounded CPU sample)",
+                   "sample_particles": n},
+        "cpu_baseline": {"value": rate, "unit": "particle-updates/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": rate, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(n, steps=3, warmup=1):
+    from oracle import port, ref
+    from ptoy_b200 import scenes
+    sc = scenes.config3(n)
+    best = None
+    for v in [v for v in ("omp", "avx_omp") if ref.available(v)] or ["port"]:
+        o = ref.RefParticles(v) if v != "port" else port.PortParticles()
+        scenes.load_into(o, sc)
+        o.step_n(warmup)
+        t0 = time.perf_counter()
+        o.step_n(steps)
+        dt = time.perf_counter() - t0
+        rate = n * steps / dt
+        if best is None or rate > best["value"]:
+            best = {"value": rate, "unit": "particle-updates/s", "cores": o.openmp_threads,
+                    "kind": "port" if v == "port" else "reference",
+                    "sample": f"configs[2] generator at n={n}, {steps} iterations after {warmup} warm-up, build={v}"}
+        o.close()
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--n", type=int, default=16_000_000, help="particles per GPU")
+    ap.add_argument("--ref-n", type=int, default=1_000_000, help="particles of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bonds", action="store_true", help="pair/gravity/walls only (configs[1]-style)")
+    args = ap.parse_args()
+    args.steps_ref = max(1, min(args.steps, 5))
+    args.warmup_ref = max(1, min(args.warmup, 1))
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import ptoy_b200
+    from ptoy_b200 import scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    W = max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- scene ---------------------------------------------------------------------------
+    t0 = time.time()
+    sc = scenes.hex_lattice(args.n, 2.02, 0.01, seed=1234 + rank) if args.no_bonds else strip_scene(args.n, rank, world)
+    n = sc.n
+    g = ptoy_b200.Particles(device=local, default_scene=False)
+    scenes.load_into(g, sc)
+    g.set_renderer_ready(False)
+    g.synchronize()
+    degree = len(sc.bonds) / n
+    bpu = bytes_per_update(degree)
+    t_setup = time.time() - t0
+
+    stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local))
+
+    # ---- device-resident throughput ("value") -----------------------------------------------
+    g.step_n(W)
+    g.synchronize()
+    l0 = g.launch_count
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    g.step_n(args.steps)
+    ev1.record(stream)
+    g.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = g.launch_count - l0
+    alive = g.num_particles
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        c = torch.tensor([float(alive), float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c)
+        alive_total, launches = int(c[0].item()), int(c[1].item())
+    else:
+        alive_total = alive
+    value = alive_total * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel durations (CUDA events on the engine's stream, same loop) ---------------------
+    g.enable_kernel_timing(True)
+    g.step_n(args.steps)
+    kt = g.kernel_times()
+    g.enable_kernel_timing(False)
+    per_launch_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in kt.items()}
+    dominant = max(("stage1", "stage2"), key=lambda k: per_launch_ms[k])
+    peak, peak_src = hbm_peak()
+    achieved = bpu[dominant] * alive / (per_launch_ms[dominant] * 1e-3) / 1e9 if per_launch_ms[dominant] else 0.0
+    step_gbs = bpu["total"] * alive_total / world * args.steps / (ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(f"{dominant}@{n}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": f"stage_kernel<{dominant[-1]}>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": bpu, "kernel_ms_per_launch": per_launch_ms,
+                "step_achieved": step_gbs, "step_frac": step_gbs / peak}
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------
+    hp = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+    hv = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+    hi = torch.empty((n,), dtype=torch.int32).pin_memory()
+    hpn, hvn, hin = hp.numpy(), hv.numpy(), hi.numpy()
+    cnt = g.download_state(hpn, hvn, hin)
+    g.upload_state(hpn[:cnt], hvn[:cnt], hin[:cnt])      # warm-up of the path
+    g.step_n(1)
+    g.download_state(hpn, hvn, hin)
+    barrier()
+    te = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        g.upload_state(hpn[:cnt], hvn[:cnt], hin[:cnt])  # H2D: pos 8 + vel 8 + id 4 B per particle
+        g.step_n(1)
+        cnt = g.download_state(hpn, hvn, hin)            # D2H: the step's result, same 20 B
+    barrier()
+    te = time.perf_counter() - te
+    if world > 1:
+        t = torch.tensor([te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    e2e = {"value": alive_total * args.e2e_steps / te, "unit": "particle-updates/s",
+           "h2d_bytes_per_step": 20 * cnt * world, "d2h_bytes_per_step": 20 * cnt * world,
+           "ms_per_step": te / args.e2e_steps * 1e3,
+           "note": "per step: ptoy_upload_state (pinned host -> device, re-binned) + ptoy_step_n(1) + ptoy_download_state"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.ref_n)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": ("configs[2]: 16M particles, hex pitch 2.02r, ~4 directed bonds/particle, 1% frozen"
+                                    if not args.no_bonds else "pair+gravity+walls only, hex pitch 2.02r"),
+                       "particles_per_gpu": n, "mean_directed_bonds": degree, "frozen": int(len(sc.frozen)),
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent strips (weak)",
+                       "l2": "inputs larger than L2 (working set %.1f GB per GPU)" % (n * 68 / 1e9),
+                       "setup_s": t_setup},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

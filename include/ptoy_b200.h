@@ -71,6 +71,17 @@ int ptoy_add_particles(ptoy_engine* h, const float* pos_xy, const float* vel_xy,
 int ptoy_add_particles_device(ptoy_engine* h, const float* d_pos_xy, const float* d_vel_xy,
                               const int32_t* d_id, size_t n);
 
+/* Replace the particle state (positions, velocities, ids) in one call while keeping bonds,
+ * frozen set, portals, walls and time: the bulk form of emptying the grid and calling
+ * blocks::AddParticles (SURVEY.md Appendix C "load a custom scene").  Host buffers; pinned
+ * memory makes the copy asynchronous. */
+int ptoy_upload_state(ptoy_engine* h, const float* pos_xy, const float* vel_xy,
+                      const int32_t* id, size_t n);
+/* Current device state in engine order (sub-cell sorted) copied straight into host buffers
+ * (cap entries each, any pointer may be NULL); *n = live particle count.  Synchronises. */
+int ptoy_download_state(ptoy_engine* h, float* pos_xy, float* vel_xy, int32_t* id,
+                        size_t cap, size_t* n);
+
 /* ---- stepping --------------------------------------------------------------------- */
 
 /* Particles::step(time_target, quit=false) (particles.cpp:93-203): iterate

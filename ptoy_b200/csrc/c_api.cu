@@ -73,6 +73,12 @@ int ptoy_add_particles(ptoy_engine* h, const float* pos, const float* vel, const
 int ptoy_add_particles_device(ptoy_engine* h, const float* pos, const float* vel, const int32_t* id, size_t n) {
   PTOY_TRY(h, E.add_particles(pos, vel, id, n, true))
 }
+int ptoy_upload_state(ptoy_engine* h, const float* pos, const float* vel, const int32_t* id, size_t n) {
+  PTOY_TRY(h, E.upload_state(pos, vel, id, n))
+}
+int ptoy_download_state(ptoy_engine* h, float* pos, float* vel, int32_t* id, size_t cap, size_t* n) {
+  PTOY_TRY(h, *n = E.download_state(pos, vel, id, cap))
+}
 int ptoy_step(ptoy_engine* h, float time_target) { PTOY_TRY(h, E.step_to(time_target)) }
 int ptoy_step_n(ptoy_engine* h, int n) { PTOY_TRY(h, E.step_n(n)) }
 int ptoy_synchronize(ptoy_engine* h) { PTOY_TRY(h, E.synchronize()) }

@@ -592,6 +592,29 @@ void Engine::add_particles(const float* pos, const float* vel, const int32_t* id
   rekey_and_reorder(0, false);
 }
 
+void Engine::upload_state(const float* pos, const float* vel, const int32_t* id, size_t n) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  prune_bonds();  // CheckBonds against the state being replaced, before it disappears
+  const int zero = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&ctr_.p->n_cur, &zero, sizeof(int), cudaMemcpyHostToDevice, stream_));
+  n_bound_ = 0;
+  slot_map_valid_ = false;
+  if (slot_of_id_.p && !bonds_.empty()) { launch_fill_i32(slot_of_id_.p, -1, id_cap_ + 1, stream_); ++launches_; }
+  add_particles(pos, vel, id, n, false);
+}
+
+size_t Engine::download_state(float* pos, float* vel, int32_t* id, size_t cap) {
+  read_counters();
+  const size_t n = std::min(cap, (size_t)h_ctr_->n_cur);
+  if (n) {
+    if (pos) CUDA_CHECK(cudaMemcpyAsync(pos, pos_[cur_].p, n * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
+    if (vel) CUDA_CHECK(cudaMemcpyAsync(vel, vel_[cur_].p, n * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
+    if (id) CUDA_CHECK(cudaMemcpyAsync(id, id_[cur_].p, n * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+  }
+  return (size_t)h_ctr_->n_cur;
+}
+
 // ---- one iteration -------------------------------------------------------------------------
 StageArgs Engine::make_stage_args(int stage) {
   StageArgs a{};

@@ -47,6 +47,8 @@ class Engine {
   void reset_scene(V2 A, V2 B);
   void load_default_scene();
   void add_particles(const float* pos, const float* vel, const int32_t* id, size_t n, bool on_device);
+  void upload_state(const float* pos, const float* vel, const int32_t* id, size_t n);
+  size_t download_state(float* pos, float* vel, int32_t* id, size_t cap);
 
   // stepping
   void step_to(float time_target);

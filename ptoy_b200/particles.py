@@ -34,6 +34,8 @@ SIGNATURES = {
     "ptoy_reset_scene": [_f, _f, _f, _f],
     "ptoy_add_particles": [_f32p, _f32p, _i32p, _sz],
     "ptoy_add_particles_device": [_vp, _vp, _vp, _sz],
+    "ptoy_upload_state": [_vp, _vp, _vp, _sz],
+    "ptoy_download_state": [_vp, _vp, _vp, _sz, _szp],
     "ptoy_step": [_f],
     "ptoy_step_n": [_i],
     "ptoy_synchronize": [],
@@ -308,6 +310,17 @@ class Particles:
 
     def add_particles_device(self, pos_ptr, vel_ptr, id_ptr, n):
         self._call("ptoy_add_particles_device", pos_ptr, vel_ptr, id_ptr, int(n))
+
+    def upload_state(self, pos, vel, ids):
+        """Replace pos/vel/id (C-contiguous float32/int32 numpy arrays, ideally pinned)."""
+        assert pos.dtype == np.float32 and vel.dtype == np.float32 and ids.dtype == np.int32
+        self._call("ptoy_upload_state", pos.ctypes.data, vel.ctypes.data, ids.ctypes.data, len(ids))
+
+    def download_state(self, pos, vel, ids):
+        """Copy the live state (engine order) into the given host arrays; returns the count."""
+        n = C.c_size_t()
+        self._call("ptoy_download_state", _ptr(pos), _ptr(vel), _ptr(ids), len(pos), C.byref(n))
+        return n.value
 
     def set_bonds(self, pairs):
         pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)

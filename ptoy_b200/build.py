@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libptoy_b200.so")
+LIB = os.environ.get("PTOY_B200_LIB", os.path.join(HERE, "libptoy_b200.so"))
 SOURCES = ["kernels.cu", "engine.cu", "c_api.cu"]
 NVCC = os.environ.get("PTOY_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -27,7 +27,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("PTOY_NVCC_EXTRA", "").split()
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
         ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -26,6 +26,9 @@ struct GridDev {
   float fdi, fdj;  // (float)dims
   int SI, SJ;      // padded sub-grid dims: 2*d + 6
   int ncell;       // SI*SJ ; key == ncell is the trash bin (particle left the grid)
+  float inv_hsx, inv_hsy;  // fl(2/bs): approximate sub-cell coordinate w~ = (x - A) * inv_hs
+  float tol;       // |w~ - w| bound used by the division-free binning (kernels.cu cell_of_fast)
+  float wmax;      // largest |w| for which tol holds
 };
 
 // Physics constants, computed on the host with the reference's own expression
@@ -37,6 +40,9 @@ struct Phys {
   int gravity_enable;
   float diss;            // kDissipation*kMass            particles.cpp:880
   float RR, thr, r2c;    // pair: fl(R*R), r^2 threshold, first r^2 with zero force
+  float r2c_hi;          // r2c grown by 8 ulp: bound for the fma prefilter of the pair loop
+  float v2c;             // largest |v|^2 whose rounded sqrt is <= kVelocityLimit
+  float bond_y;          // fl(1/bondR)
   float radius;          // kRadius
   float RRw;             // wall: fl(r*r)                 particles.cpp:574-578
   float wall_reach;      // conservative |p-Q| beyond which F12wall is exactly 0
@@ -91,6 +97,7 @@ struct StageArgs {
   float2* pos_out;       // stage 2: x' (may alias pos)
   float2* vel_out;       // stage 2: v'
   const int* id;
+  const unsigned* cell;  // packed sub-cell (Si << 16 | Sj) of every sorted particle
   const int* start;      // [ncell+2] exclusive prefix of sub-cell populations
   float margin;          // extra search margin in sub-cell units
   // frozen_ as a bitmask over ids
@@ -101,6 +108,9 @@ struct StageArgs {
   const int* bond_col;
   const int* slot_of_id;
   int has_bonds;
+  int* bslot;                  // [kBondPlan][cap] bond partner slots: written by stage 1, read by stage 2
+  unsigned char* bdeg;         // min(bond degree, 255), same hand-over
+  int cap;                     // stride of the slot-major bslot array
   // portals
   int n_sides;           // 2 * pairs
   const PortalSide* sides;
@@ -110,7 +120,7 @@ struct StageArgs {
   int need_id;
   // outputs
   float2* force_out;     // optional, by slot
-  int* newkey;           // stage 2
+  unsigned* newcell;     // stage 2: packed sub-cell after the update (old slot order)
   int* cnt;              // stage 2: sub-cell histogram (RED)
   int do_tail;           // stage 2: teleport + key + histogram fused
   int write_state;       // 0 = forces only (debug)
@@ -129,14 +139,15 @@ struct TailArgs {  // standalone teleport + key pass (resize iterations, add_par
   const uint8_t* blk_flags;
   int do_teleport;
   int first;     // particles [first, n) are processed
-  int* newkey;
+  unsigned* newcell;
   int* cnt;
 };
 
 struct ReorderArgs {
   const Counters* ctr;
   int ncell;
-  const int* newkey;
+  int SJ;
+  const unsigned* newcell;
   const int* start;
   int* cnt;          // histogram on entry; fill counts it down to zero
   int* order;        // order[new slot] = old slot (nondeterministic within a cell)
@@ -146,6 +157,7 @@ struct ReorderArgs {
   float2* pos_out;
   float2* vel_out;
   int* id_out;
+  unsigned* cell_out;
   int* slot_of_id;   // optional
 };
 

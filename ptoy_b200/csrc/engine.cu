@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -87,7 +88,7 @@ template struct DevBuf<unsigned long long>;
 template struct DevBuf<Counters>;
 template struct DevBuf<uint32_t>;
 template struct DevBuf<PortalSide>;
-template struct DevBuf<uint8_t>;
+template struct DevBuf<uint8_t>;  // also unsigned char
 
 // ---- construction --------------------------------------------------------------------
 Engine::Engine(int device) : device_(device) {
@@ -159,12 +160,17 @@ void Engine::alloc_cells() {
   const long long SI = 2ll * di_ + 6, SJ = 2ll * dj_ + 6;
   const long long ncell = SI * SJ;
   if (ncell + 8 >= (1ll << 31)) throw Error(-4, "sub-cell grid exceeds 2^31 cells");
+  if (SI > 65535 || SJ > 65535) throw Error(-4, "block grid exceeds 32764 blocks per axis");
   grid_.Ax = gA_.x; grid_.Ay = gA_.y;
   grid_.bsx = bs_.x; grid_.bsy = bs_.y;
   grid_.di = di_; grid_.dj = dj_;
   grid_.fdi = (float)di_; grid_.fdj = (float)dj_;
   grid_.SI = (int)SI; grid_.SJ = (int)SJ;
   grid_.ncell = (int)ncell;
+  grid_.inv_hsx = 2.0f / bs_.x;
+  grid_.inv_hsy = 2.0f / bs_.y;
+  grid_.wmax = (float)std::max(SI, SJ) + 8.f;
+  grid_.tol = grid_.wmax * std::ldexp(1.f, -21);  // >= 2 * |w| * 2^-22 for |w| < wmax
   n_items_ = (int)(((ncell + 2) + 3) / 4 * 4);
   cnt_.alloc((size_t)n_items_);
   start_.alloc((size_t)n_items_ + 4);
@@ -179,7 +185,7 @@ void Engine::alloc_cells() {
   blk_flags_.alloc((size_t)di_ * dj_);
   // search margins in sub-cell units
   const float W = (float)std::max(SI, SJ);
-  margin1_ = std::ldexp(1.f, -19) + W * std::ldexp(1.f, -21);
+  margin1_ = std::ldexp(1.f, -19) + W * std::ldexp(1.f, -21) + grid_.tol;
   const float drift = kVelocityLimit * dt_ * 0.5f;
   margin2_ = margin1_ + 2.f * drift / (0.5f * bs_.x) * 1.001f + W * std::ldexp(1.f, -21);
   if (!(margin2_ < 0.5f)) throw Error(-2, "time step too large for the sub-cell search margin");
@@ -196,7 +202,10 @@ void Engine::ensure_capacity(size_t n) {
   }
   pos_h_.alloc(nc);
   vel_h_.alloc(nc);
-  newkey_.alloc(nc);
+  newcell_.alloc(nc);
+  bslot_.alloc(nc * 6);
+  bdeg_.alloc(nc);
+  for (int k = 0; k < 2; ++k) cell_[k].alloc(nc);  // rewritten by every reorder before use
   order_.alloc(nc);
   force_dbg_.release();
   cap_ = nc;
@@ -291,6 +300,24 @@ void Engine::update_portal_blocks(PortalHost& p) const {
     }
 }
 
+// largest float v2 with fl(sqrt(v2)) <= limit (sqrt is monotone): bisection on the bit pattern
+static float find_v2c(float limit) {
+  auto over = [&](float v2) { return (float)std::sqrt((double)v2) > limit; };
+  uint32_t lo, hi;
+  float a = limit * limit * 0.5f, b = limit * limit * 2.f;
+  std::memcpy(&lo, &a, 4);
+  std::memcpy(&hi, &b, 4);
+  while (hi - lo > 1) {  // invariant: !over(lo), over(hi)
+    uint32_t mid = lo + (hi - lo) / 2;
+    float m;
+    std::memcpy(&m, &mid, 4);
+    if (over(m)) hi = mid; else lo = mid;
+  }
+  float r;
+  std::memcpy(&r, &lo, 4);
+  return r;
+}
+
 static float find_r2c(float thr, float RR) {
   // smallest float r2 >= thr for which F12's coefficient is clamped to zero, i.e.
   // fl(fl(1/r2) * RR) > 1 fails (see kernels.cu pair_force).  Monotone -> bisection on bits.
@@ -325,6 +352,8 @@ Phys Engine::make_phys() const {
   p.RR = R * R;
   p.thr = (float)(std::pow((double)kRadius, 2) * 1e-3);
   p.r2c = r2c_;
+  p.r2c_hi = r2c_ * (1.0f + 8.0f * std::ldexp(1.f, -23));
+  p.v2c = v2c_;
   p.radius = kRadius;
   p.RRw = kRadius * kRadius;
   p.wall_reach = wall_reach_;
@@ -332,6 +361,7 @@ Phys Engine::make_phys() const {
   p.RRe = Re * Re;
   p.vlimit = kVelocityLimit;
   p.bondR = R;
+  p.bond_y = (float)(1. / (double)R);
   p.bond_cutoff = (float)(8. * (double)kRadius);
   p.sigma_bond = kSigmaBond;
   p.bond_portal_reach = 2. * (double)kPortalThickness + (double)p.bond_cutoff;
@@ -356,6 +386,7 @@ void Engine::sync_env() {
   if (r2c_ == 0.f) {
     const float R = (float)(2. * (double)kRadius);
     r2c_ = find_r2c((float)(std::pow((double)kRadius, 2) * 1e-3), R * R);
+    v2c_ = find_v2c(kVelocityLimit);
   }
   // --- walls: force is exactly zero when |p - Q| >= r(1 + 2^-22); Q and the differences
   // carry rounding errors of a few ulp of the coordinates, so grow by 16 ulp of the
@@ -635,12 +666,15 @@ StageArgs Engine::make_stage_args(int stage) {
   a.frozen_bits = frozen_bits_.p;
   a.has_bonds = !bonds_.empty();
   a.bond_ptr = bond_ptr_.p; a.bond_col = bond_col_.p; a.slot_of_id = slot_of_id_.p;
+  a.bslot = bslot_.p; a.bdeg = bdeg_.p;
+  a.cap = (int)cap_;
   a.n_sides = has_portal_tables_ ? (int)portals_.size() * 2 : 0;
   a.sides = sides_.p; a.pblk_ptr = pblk_ptr_.p; a.pblk = pblk_.p;
   a.blk_flags = has_portal_tables_ ? blk_flags_.p : nullptr;
   a.need_id = a.has_frozen || a.has_bonds || pick_enabled_;
   a.force_out = nullptr;
-  a.newkey = newkey_.p; a.cnt = cnt_.p;
+  a.newcell = newcell_.p; a.cnt = cnt_.p;
+  a.cell = cell_[cur_].p;
   a.do_tail = 1;
   a.write_state = 1;
   return a;
@@ -693,7 +727,9 @@ void Engine::reorder() {
   ReorderArgs r{};
   r.ctr = ctr_.p;
   r.ncell = grid_.ncell;
-  r.newkey = newkey_.p;
+  r.newcell = newcell_.p;
+  r.SJ = grid_.SJ;
+  r.cell_out = cell_[cur_ ^ 1].p;
   r.start = start_.p;
   r.cnt = cnt_.p;
   r.order = order_.p;
@@ -725,7 +761,7 @@ void Engine::rekey_and_reorder(int first, bool teleport) {
   a.blk_flags = has_portal_tables_ ? blk_flags_.p : nullptr;
   a.do_teleport = teleport && a.n_sides > 0;
   a.first = first;
-  a.newkey = newkey_.p; a.cnt = cnt_.p;
+  a.newcell = newcell_.p; a.cnt = cnt_.p;
   begin_timed(5);
   launch_tail(a, n_bound_, stream_);
   end_timed();
@@ -912,8 +948,8 @@ void Engine::eval_forces(int stage, size_t id_cap, float* force) {
   CUDA_CHECK(cudaSetDevice(device_));
   if (stage != 1 && stage != 2) throw Error(-2, "stage must be 1 or 2");
   sync_env(); sync_bonds(); sync_frozen();
-  if (!bonds_.empty()) ensure_slot_map();
   read_counters();
+  if (!bonds_.empty()) ensure_slot_map();
   force_dbg_.alloc(std::max<size_t>(cap_, 1));
   const size_t m = std::max(id_cap, id_cap_) + 1;
   DevBuf<float2> by_id;

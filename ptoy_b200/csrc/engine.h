@@ -147,7 +147,10 @@ class Engine {
   size_t id_cap_ = 0;
   int cur_ = 0;         // which of the ping-pong buffers holds the sorted state
   DevBuf<float2> pos_[2], vel_[2], pos_h_, vel_h_, force_dbg_;
-  DevBuf<int> id_[2], newkey_, order_;
+  DevBuf<int> id_[2], order_;
+  DevBuf<uint32_t> cell_[2], newcell_;
+  DevBuf<int> bslot_;            // bond partner slots, slot-major: stage 1 -> stage 2
+  DevBuf<unsigned char> bdeg_;
   DevBuf<int> cnt_, start_;
   int n_items_ = 0;     // padded scan length
   DevBuf<unsigned long long> tile_state_;
@@ -167,7 +170,7 @@ class Engine {
   float wall_reach_ = 0.f;
   WallDev walls_dev_[kMaxWalls];
   float free_box_[4];
-  float r2c_ = 0.f;
+  float r2c_ = 0.f, v2c_ = 0.f;
   float margin1_ = 0.f, margin2_ = 0.f;
 
   // timing

@@ -16,6 +16,10 @@
 //   gather_kernel    deterministic (stable) reorder of pos/vel/id + id->slot map
 #include "common.h"
 
+#ifndef PTOY_STAGE_MINB
+#define PTOY_STAGE_MINB 4  // resident CTAs per SM the stage kernels are compiled for
+#endif
+
 namespace ptoy {
 
 // ---------------------------------------------------------------------------------
@@ -27,7 +31,7 @@ __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 // (float)(1. / (double)x): double division then rounding to float equals the
 // correctly rounded float quotient (53 >= 2*24+2), i.e. __fdiv_rn(1, x).
-__device__ __forceinline__ float rcp_exact(float x) { return __fdiv_rn(1.0f, x); }
+__device__ __forceinline__ float rcp_exact(float x) { return __frcp_rn(x); }
 // geometry.h:62-64  dot = v.x*x + v.y*y
 __device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) {
   return fadd(fmul(ax, bx), fmul(ay, by));
@@ -35,6 +39,16 @@ __device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) {
 // geometry.h:65-67  length = sqrt(x*x + y*y) (double sqrt of a float, rounded back:
 // identical to the correctly rounded float sqrt)
 __device__ __forceinline__ float len2(float x, float y) { return __fsqrt_rn(dot2(x, y, x, y)); }
+// r / R for the constant R = 2r = 0.04f (particles.cpp:729,733).  With y = fl(1/R) = 25 exactly,
+// q0 = fl(r*y), rem = fma(-q0, R, r), q1 = fma(rem, y, q0) is the correctly rounded quotient
+// (Markstein); checked exhaustively against r / R for every float r in [1e-30, 1e30]
+// (scripts/check_exact_tricks.c).  The fused multiply-adds are part of the division algorithm,
+// not contractions of reference operations.
+__device__ __forceinline__ float div_by_bondR(float r, float R, float y) {
+  const float q0 = __fmul_rn(r, y);
+  const float rem = __fmaf_rn(-q0, R, r);
+  return __fmaf_rn(rem, y, q0);
+}
 // std::max<float>(0, k) = (0 < k) ? k : 0   (NaN -> 0)
 __device__ __forceinline__ float max0(float k) { return (0.0f < k) ? k : 0.0f; }
 
@@ -61,9 +75,39 @@ __device__ __forceinline__ Cell cell_of(const GridDev& g, float2 p) {
   c.uj = wy - fy;
   return c;
 }
-__device__ __forceinline__ int block_of(const GridDev& g, const Cell& c) {
-  const int bi = max(0, (c.Si - 4) >> 1), bj = max(0, (c.Sj - 4) >> 1);
+// Same result as cell_of() without the two IEEE divisions in the common case:
+// w~ = fl((x - A) * fl(2/bs)) differs from the exact w = 2*fl(fl(x - A)/bs) by less than
+// |w| * 2^-22, so floor(w~) == floor(w) unless w~ lies within g.tol (>= 2 * wmax * 2^-22) of an
+// integer; those few particles take the exact path.  (ui, uj are then approximate by < tol,
+// which the search margin absorbs.)
+__device__ __forceinline__ Cell cell_of_fast(const GridDev& g, float2 p) {
+  const float wx = fsub(p.x, g.Ax) * g.inv_hsx, wy = fsub(p.y, g.Ay) * g.inv_hsy;
+  const float fx = floorf(wx), fy = floorf(wy);
+  const float ux = wx - fx, uy = wy - fy;
+  const float hi = 1.0f - g.tol;
+  const bool safe = ux > g.tol && ux < hi && uy > g.tol && uy < hi &&
+                    fabsf(wx) < g.wmax && fabsf(wy) < g.wmax;  // false for NaN
+  if (!safe) return cell_of(g, p);
+  Cell c;
+  c.valid = fx >= -2.0f && fx < 2.0f * g.fdi && fy >= -2.0f && fy < 2.0f * g.fdj;
+  c.Si = (int)fx + 4;
+  c.Sj = (int)fy + 4;
+  c.ui = ux;
+  c.uj = uy;
+  return c;
+}
+__device__ __forceinline__ int block_of_s(const GridDev& g, int Si, int Sj) {
+  const int bi = max(0, (Si - 4) >> 1), bj = max(0, (Sj - 4) >> 1);
   return bi * g.dj + bj;
+}
+__device__ __forceinline__ int block_of(const GridDev& g, const Cell& c) { return block_of_s(g, c.Si, c.Sj); }
+// packed sub-cell of a particle: Si << 16 | Sj ; kTrashCell = left the grid
+constexpr unsigned kTrashCell = 0xffffffffu;
+__device__ __forceinline__ unsigned pack_cell(const Cell& c) {
+  return c.valid ? ((unsigned)c.Si << 16) | (unsigned)c.Sj : kTrashCell;
+}
+__device__ __forceinline__ int key_of_packed(unsigned p, int SJ, int ncell) {
+  return p == kTrashCell ? ncell : (int)(p >> 16) * SJ + (int)(p & 0xffffu);
 }
 // sub-rows / sub-columns (inclusive) that make up reference block `blk`
 __device__ __forceinline__ void block_extent(const GridDev& g, int blk, int& r0, int& r1, int& c0, int& c1) {
@@ -108,7 +152,7 @@ __device__ __forceinline__ void bond_force(const Phys& ph, float px, float py, f
   // k = max(1. - r/R, 1. - 5) in double, rounded to float.  1 - x is exact in
   // double for float x >= 2^-29 and rounds to 1.0f either way below that, so
   // the float subtraction gives the same float; -4 is exact.
-  const float q = fdiv(r, ph.bondR);
+  const float q = div_by_bondR(r, ph.bondR, ph.bond_y);
   float k = fsub(1.0f, q);
   k = (k < -4.0f) ? -4.0f : k;  // std::max(a, b) = (a < b) ? b : a
   const float s = fmul(ph.sigma_bond, k);
@@ -157,9 +201,28 @@ __device__ __forceinline__ bool in_sorted(const int* __restrict__ list, int n, i
 // all forces on one particle (particles.cpp:839-910 calc_forces, :761-826 RHS_bonds,
 // :318-381 ApplyPortalsForces), summed in the reference's order of force kinds
 // ---------------------------------------------------------------------------------
+constexpr int kHitQueue = 6;     // pending in-range pairs per thread (shared memory)
+constexpr int kBondPlan = 6;     // bond partners per particle resolved up front / handed from stage 1 to stage 2
+struct HitQueue {
+  float dx[kHitQueue][kThreads];
+  float dy[kHitQueue][kThreads];
+};
+
+// One queued pair: the exact r^2 (reference rounding) decides, the prefilter only proposed it.
+__device__ __forceinline__ void eval_hit(const Phys& ph, float dx, float dy, float& fx, float& fy) {
+  const float r2 = dot2(dx, dy, dx, dy);
+  if (r2 < ph.r2c) {
+    float px, py;
+    pair_force(ph, dx, dy, r2, px, py);
+    fx = fadd(fx, px);
+    fy = fadd(fy, py);
+  }
+}
+
+template <int STAGE>
 __device__ __forceinline__ float2 particle_force(
-    const StageArgs& a, const float2* __restrict__ X, int slot, int pid, float2 x, float2 v,
-    const Cell& c, int blk, unsigned flags) {
+    const StageArgs& a, const float2* __restrict__ X, HitQueue& hq, int slot, int pid, float2 x, float2 v,
+    int Si, int Sj, float ui, float uj, int blk, unsigned flags) {
   const Phys& ph = a.ph;
   float fx = 0.0f, fy = 0.0f;
   if (ph.gravity_enable) { fx = ph.gfx; fy = ph.gfy; }                       // :849-851
@@ -205,25 +268,82 @@ __device__ __forceinline__ float2 particle_force(
   fx = fsub(fx, fmul(v.x, ph.diss));                                         // :880
   fy = fsub(fy, fmul(v.y, ph.diss));
 
-  // ---- pair loop (:884-900 + :598-606) over the sub-cell neighbourhood ----------
+  // ---- bonds, part 1: partner slots and positions, fetched before the pair search starts so
+  // the loads overlap it.  Stage 1 resolves id -> CSR row -> partner id -> slot (three dependent
+  // gather levels, issued as batches of independent loads) and records the slots slot-major;
+  // stage 2 (same sorted order, same partners) just reads them back coalesced.
+  int nb = 0;
+  float2 bpos[kBondPlan];
+  int bslot[kBondPlan];
+  if (a.has_bonds) {
+    if (STAGE == 1) {
+      const unsigned e0 = __ldg(a.bond_ptr + pid);
+      const unsigned ne = __ldg(a.bond_ptr + pid + 1) - e0;
+      nb = (int)(ne < 255u ? ne : 255u);
+      int bcol[kBondPlan];
+#pragma unroll
+      for (int k = 0; k < kBondPlan; ++k) bcol[k] = (k < nb) ? __ldg(a.bond_col + e0 + k) : -1;
+#pragma unroll
+      for (int k = 0; k < kBondPlan; ++k) bslot[k] = (bcol[k] >= 0) ? a.slot_of_id[bcol[k]] : -1;
+      if (a.bslot) {
+#pragma unroll
+        for (int k = 0; k < kBondPlan; ++k)
+          if (k < nb) a.bslot[(size_t)k * a.cap + slot] = bslot[k];
+        a.bdeg[slot] = (unsigned char)nb;
+      }
+    } else {
+      nb = a.bdeg[slot];
+#pragma unroll
+      for (int k = 0; k < kBondPlan; ++k) bslot[k] = (k < nb) ? __ldg(a.bslot + (size_t)k * a.cap + slot) : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < kBondPlan; ++k) bpos[k] = (bslot[k] >= 0) ? __ldg(X + bslot[k]) : make_float2(0.f, 0.f);
+  }
+
+  // ---- pair forces (:884-900 + :598-606) over the sub-cell neighbourhood ----------------
+  // Candidates are only TESTED in the loop, with a cheap conservative prefilter
+  // (fma(dx,dx,dy*dy) against r2c grown by a few ulp); the few that pass are queued per thread
+  // in shared memory and evaluated afterwards with the reference's exact arithmetic, so the
+  // divergent force evaluation runs once per queued pair instead of once per loop iteration in
+  // which any lane had a hit.  The queue is FIFO: contributions are summed in candidate order.
+  // The particle itself (skipped by address in the reference) is excluded by splitting its own
+  // row's range around its slot.
   {
-    const int r_lo = c.Si - 1 - (c.ui < a.margin), r_hi = c.Si + 1 + (c.ui > 1.0f - a.margin);
-    const int c_lo = c.Sj - 1 - (c.uj < a.margin), c_hi = c.Sj + 1 + (c.uj > 1.0f - a.margin);
+    const int t = threadIdx.x;
+    int nq = 0;
+    const int r_lo = Si - 1 - (ui < a.margin), r_hi = Si + 1 + (ui > 1.0f - a.margin);
+    const int c_lo = Sj - 1 - (uj < a.margin), c_hi = Sj + 1 + (uj > 1.0f - a.margin);
+    auto test = [&](float2 pq) {
+      const float dx = fsub(x.x, pq.x), dy = fsub(x.y, pq.y);
+      const float r2a = __fmaf_rn(dx, dx, dy * dy);
+      if (r2a < ph.r2c_hi) {
+        hq.dx[nq][t] = dx; hq.dy[nq][t] = dy;
+        if (++nq == kHitQueue) {
+#pragma unroll
+          for (int k = 0; k < kHitQueue; ++k) eval_hit(ph, hq.dx[k][t], hq.dy[k][t], fx, fy);
+          nq = 0;
+        }
+      }
+    };
+    auto scan = [&](int q, int end) {
+      for (; q + 1 < end; q += 2) {
+        const float2 p0 = __ldg(X + q), p1 = __ldg(X + q + 1);
+        test(p0);
+        test(p1);
+      }
+      if (q < end) test(__ldg(X + q));
+    };
     for (int R = r_lo; R <= r_hi; ++R) {
       const int base = R * a.g.SJ;
       const int beg = __ldg(a.start + base + c_lo), end = __ldg(a.start + base + c_hi + 1);
-      for (int q = beg; q < end; ++q) {
-        const float2 pq = X[q];
-        const float dx = fsub(x.x, pq.x), dy = fsub(x.y, pq.y);
-        const float r2 = dot2(dx, dy, dx, dy);
-        if (r2 < ph.r2c && q != slot) {
-          float px, py;
-          pair_force(ph, dx, dy, r2, px, py);
-          fx = fadd(fx, px);
-          fy = fadd(fy, py);
-        }
+      if (R == Si) {
+        scan(beg, slot);
+        scan(slot + 1, end);
+      } else {
+        scan(beg, end);
       }
     }
+    for (int k = 0; k < nq; ++k) eval_hit(ph, hq.dx[k][t], hq.dy[k][t], fx, fy);
   }
 
   // ---- walls (:903-909); exact zero outside each wall's grown bbox ----------------
@@ -240,15 +360,15 @@ __device__ __forceinline__ float2 particle_force(
     }
   }
 
-  // ---- bonds (:761-826), CSR row of this id, partners ascending ------------------
+  // ---- bonds, part 2 (:761-826): CSR row of this id, partners ascending ----------------
   if (a.has_bonds) {
-    const unsigned e0 = a.bond_ptr[pid], e1 = a.bond_ptr[pid + 1];
-    for (unsigned e = e0; e < e1; ++e) {
-      const int sb = a.slot_of_id[a.bond_col[e]];
-      if (sb < 0) continue;  // partner left the grid: bond erased by CheckBonds (:205-215)
-      const float2 q = X[sb];
+    auto one_bond = [&](int sb, float2 q) {
+      if (sb < 0) return;  // partner left the grid: bond erased by CheckBonds (:205-215)
       float bx, by;
-      const float dist = len2(fsub(q.x, x.x), fsub(q.y, x.y));               // p_pos.dist(q_pos)
+      // p_pos.dist(q_pos) = |q - p| and F12_bond's |p - q| are the same float: the differences
+      // are exact negatives of each other, so one sqrt serves both (particles.cpp:731,779)
+      const float ddx = fsub(x.x, q.x), ddy = fsub(x.y, q.y);
+      const float dist = len2(ddx, ddy);
       bool found = false;
       if (!(dist < ph.bond_cutoff)) {                                        // :784-819
         for (int s = 0; s < a.n_sides; ++s) {
@@ -268,9 +388,25 @@ __device__ __forceinline__ float2 particle_force(
           }
         }
       }
-      if (!found) bond_force(ph, x.x, x.y, q.x, q.y, bx, by);
+      if (!found) {                                                          // :727-736 inlined
+        float k = fsub(1.0f, div_by_bondR(dist, ph.bondR, ph.bond_y));
+        k = (k < -4.0f) ? -4.0f : k;
+        const float sk = fmul(ph.sigma_bond, k);
+        bx = fmul(ddx, sk);
+        by = fmul(ddy, sk);
+      }
       fx = fadd(fx, bx);
       fy = fadd(fy, by);
+    };
+#pragma unroll
+    for (int k = 0; k < kBondPlan; ++k)
+      if (k < nb) one_bond(bslot[k], bpos[k]);
+    if (nb > kBondPlan) {  // more partners than the plan holds: walk the rest of the CSR row
+      const unsigned e0 = __ldg(a.bond_ptr + pid), ne = __ldg(a.bond_ptr + pid + 1) - e0;
+      for (unsigned e = kBondPlan; e < ne; ++e) {
+        const int sb = a.slot_of_id[a.bond_col[e0 + e]];
+        one_bond(sb, sb >= 0 ? __ldg(X + sb) : make_float2(0.f, 0.f));
+      }
     }
   }
 
@@ -340,9 +476,12 @@ __device__ __forceinline__ float2 particle_force(
 }
 
 // particles.cpp:117-120: if (|v| > limit) v *= limit / |v|
+// fl(sqrt(v2)) > limit  <=>  v2 > v2c (sqrt is monotone; v2c found by bisection on the host), so
+// the square root is only taken when the clamp fires.
 __device__ __forceinline__ void clamp_velocity(const Phys& ph, float& vx, float& vy) {
-  const float l = len2(vx, vy);
-  if (l > ph.vlimit) {
+  const float v2 = dot2(vx, vy, vx, vy);
+  if (v2 > ph.v2c) {
+    const float l = __fsqrt_rn(v2);
     const float s = fdiv(ph.vlimit, l);
     vx = fmul(vx, s);
     vy = fmul(vy, s);
@@ -387,15 +526,14 @@ __device__ __forceinline__ void teleport(const A& a, int blk, float2& x, float2&
   }
 }
 
-__device__ __forceinline__ void key_and_count(const GridDev& g, float2 x, int slot, int* newkey, int* cnt) {
-  const Cell nc = cell_of(g, x);
-  const int key = nc.valid ? nc.Si * g.SJ + nc.Sj : g.ncell;
-  newkey[slot] = key;
-  atomicAdd(cnt + key, 1);  // result unused -> RED.ADD
+__device__ __forceinline__ void key_and_count(const GridDev& g, float2 x, int slot, unsigned* newcell, int* cnt) {
+  const unsigned pc = pack_cell(cell_of_fast(g, x));
+  newcell[slot] = pc;
+  atomicAdd(cnt + key_of_packed(pc, g.SJ, g.ncell), 1);  // result unused -> RED.ADD
 }
 
 template <int STAGE>
-__global__ void __launch_bounds__(kThreads) stage_kernel(const __grid_constant__ StageArgs a) {
+__global__ void __launch_bounds__(kThreads, PTOY_STAGE_MINB) stage_kernel(const __grid_constant__ StageArgs a) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.ctr->n_cur) return;
   const float2 x0 = a.pos[i];
@@ -403,12 +541,19 @@ __global__ void __launch_bounds__(kThreads) stage_kernel(const __grid_constant__
   float2 x, v;
   if (STAGE == 1) { x = x0; v = v0; } else { x = a.pos_h[i]; v = a.vel_h[i]; }
   const float2* __restrict__ X = (STAGE == 1) ? a.pos : (const float2*)a.pos_h;
-  const Cell c = cell_of(a.g, x0);
-  const int blk = block_of(a.g, c);
-  const unsigned flags = a.blk_flags ? a.blk_flags[blk] : 0u;
+  __shared__ HitQueue hq;
+  // the sub-cell this particle was binned into (stored by the reorder), and its approximate
+  // fractional position inside it (only compared against the search margin)
+  const unsigned pc = a.cell[i];
+  const int Si = (int)(pc >> 16), Sj = (int)(pc & 0xffffu);
+  const float ui = fsub(x0.x, a.g.Ax) * a.g.inv_hsx - (float)(Si - 4);
+  const float uj = fsub(x0.y, a.g.Ay) * a.g.inv_hsy - (float)(Sj - 4);
+  int blk = 0;
+  unsigned flags = 0u;
+  if (a.blk_flags) { blk = block_of_s(a.g, Si, Sj); flags = a.blk_flags[blk]; }
   const int pid = a.need_id ? a.id[i] : 0;
 
-  float2 f = particle_force(a, X, i, pid, x, v, c, blk, flags);
+  float2 f = particle_force<STAGE>(a, X, hq, i, pid, x, v, Si, Sj, ui, uj, blk, flags);
 
   bool frozen = false;
   if (a.has_frozen) frozen = (a.frozen_bits[pid >> 5] >> (pid & 31)) & 1u;
@@ -437,7 +582,7 @@ __global__ void __launch_bounds__(kThreads) stage_kernel(const __grid_constant__
     float2 vn = make_float2(vx, vy);
     if (a.do_tail) {
       if (flags & 1u) teleport(a, blk, xn, vn);
-      key_and_count(a.g, xn, i, a.newkey, a.cnt);
+      key_and_count(a.g, xn, i, a.newcell, a.cnt);
     }
     a.pos_out[i] = xn;
     a.vel_out[i] = vn;
@@ -460,13 +605,13 @@ __global__ void __launch_bounds__(kThreads) tail_kernel(const __grid_constant__ 
       a.vel[i] = v;
     }
   }
-  key_and_count(a.g, x, i, a.newkey, a.cnt);
+  key_and_count(a.g, x, i, a.newcell, a.cnt);
 }
 
 // ---------------------------------------------------------------------------------
 // single-pass exclusive scan (decoupled look-back), 1024 ints per tile
 // ---------------------------------------------------------------------------------
-constexpr int kScanItems = 4;
+constexpr int kScanItems = 16;  // consecutive ints per thread (4 x int4)
 constexpr int kScanTile = kThreads * kScanItems;
 int scan_tile_items() { return kScanTile; }
 
@@ -480,11 +625,16 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(
   __syncthreads();
   const int tile = s_tile;
   const int base = tile * kScanTile + threadIdx.x * kScanItems;
-  int4 v = make_int4(0, 0, 0, 0);
-  if (base < n_items) {  // n_items is padded to a multiple of 4
-    v = *reinterpret_cast<const int4*>(cnt + base);
+  int v[kScanItems];
+#pragma unroll
+  for (int k = 0; k < kScanItems; k += 4) {
+    int4 q = make_int4(0, 0, 0, 0);
+    if (base + k < n_items) q = *reinterpret_cast<const int4*>(cnt + base + k);  // n_items % 4 == 0
+    v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
   }
-  const int tsum = v.x + v.y + v.z + v.w;
+  int tsum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { const int t = v[k]; v[k] = tsum; tsum += t; }  // exclusive in thread
   int incl = tsum;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -523,7 +673,7 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(
         const unsigned long long f = s >> 32;
         if (f == (tag | 2ull)) { prefix += (int)(unsigned)s; break; }
         if (f == (tag | 1ull)) { prefix += (int)(unsigned)s; --t; continue; }
-        // not published yet: spin
+        // not published yet: spin (tickets are handed out in order, so tile t is running)
       }
       st[tile] = ((tag | 2ull) << 32) | (unsigned)(prefix + block_total);
       s_prefix = prefix;
@@ -532,15 +682,21 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(
   }
   __syncthreads();
   const int e0 = s_prefix + excl_in_block;
-  if (base < n_items) {
-    const int4 o = make_int4(e0, e0 + v.x, e0 + v.x + v.y, e0 + v.x + v.y + v.z);
-    *reinterpret_cast<int4*>(start + base) = o;
-    // totals: start[ncell] = alive, start[ncell+1] = alive + trash
-    const int o_arr[5] = {o.x, o.y, o.z, o.w, e0 + tsum};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (base + k == ncell) { ctr->n_next = o_arr[k]; ctr->n_total = o_arr[k + 1]; }
-    }
+  for (int k = 0; k < kScanItems; k += 4) {
+    if (base + k < n_items)
+      *reinterpret_cast<int4*>(start + base + k) = make_int4(e0 + v[k], e0 + v[k + 1], e0 + v[k + 2], e0 + v[k + 3]);
+  }
+  // totals: start[ncell] = alive, start[ncell+1] = alive + trash
+  if (ncell >= base && ncell < base + kScanItems) {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k == ncell) ctr->n_next = e0 + v[k];
+  }
+  if (ncell + 1 >= base && ncell + 1 < base + kScanItems) {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k == ncell + 1) ctr->n_total = e0 + v[k];
   }
 }
 
@@ -550,7 +706,7 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(
 __global__ void __launch_bounds__(kThreads) fill_kernel(const __grid_constant__ ReorderArgs a) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.ctr->n_cur) return;
-  const int key = a.newkey[i];
+  const int key = key_of_packed(a.newcell[i], a.SJ, a.ncell);
   // counting down leaves the histogram all-zero again for the next iteration
   const int r = atomicSub(a.cnt + key, 1) - 1;
   a.order[a.start[key] + r] = i;
@@ -567,7 +723,8 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const __grid_constant_
     if (a.slot_of_id) a.slot_of_id[a.id_in[src]] = -1;
     return;
   }
-  const int c = a.newkey[src];
+  const unsigned pc = a.newcell[src];
+  const int c = key_of_packed(pc, a.SJ, a.ncell);
   const int beg = a.start[c], end = a.start[c + 1];
   if (end - beg > 1) {
     const int want = k - beg;
@@ -582,6 +739,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const __grid_constant_
   a.vel_out[k] = a.vel_in[src];
   const int pid = a.id_in[src];
   a.id_out[k] = pid;
+  a.cell_out[k] = pc;
   if (a.slot_of_id) a.slot_of_id[pid] = k;
 }
 

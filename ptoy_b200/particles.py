@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptoy_b200.so")
+LIB_PATH = os.environ.get("PTOY_B200_LIB", os.path.join(_HERE, "libptoy_b200.so"))
 _lib = None
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")

@@ -225,13 +225,15 @@ def sc_dims(sc):
 def test_particles_leaving_the_grid_are_removed_with_their_bonds():
     """blocks.h:230-232 (silent removal) + CheckBonds (particles.cpp:205-215)."""
     g, o = gpu(default_scene=False), best_oracle()
-    pos = np.array([[1.05, 0.0], [0.0, 0.0], [0.039, 0.0], [-1.06, -0.5], [0.5, 0.5]], np.float32)
-    vel = np.array([[9.0, 0.0], [0, 0], [0, 0], [-9.0, 0.0], [0, 0]], np.float32)
-    bonds = np.array([[0, 1], [1, 0], [1, 2], [2, 1], [3, 4], [4, 3]], np.int32)
+    # 0 and 5 start outside the right wall (inside the grid's slack) and fly out together, bonded
+    # to each other; 3 leaves on the left; 1-2 stay, bonded
+    pos = np.array([[1.05, 0.0], [0.0, 0.0], [0.039, 0.0], [-1.06, -0.5], [0.5, 0.5], [1.05, 0.0405]], np.float32)
+    vel = np.array([[9.0, 0.0], [0, 0], [0, 0], [-9.0, 0.0], [0, 0], [9.0, 0.0]], np.float32)
+    bonds = np.array([[0, 5], [5, 0], [1, 2], [2, 1]], np.int32)
     for p in (g, o):
         p.reset_scene((-1, -1, 1, 1))
         p.set_gravity(False)
-        p.add_particles(pos, vel, np.arange(5, dtype=np.int32))
+        p.add_particles(pos, vel, np.arange(6, dtype=np.int32))
         p.set_bonds(bonds)
     g.set_renderer_ready(False)
     for k in range(30):
@@ -239,7 +241,7 @@ def test_particles_leaving_the_grid_are_removed_with_their_bonds():
         o.step_n(1)
         assert g.num_particles == o.num_particles, k
         assert np.array_equal(g.get_bonds(), o.get_bonds()), k
-        sg, so = g.state_by_id(5), o.state_by_id(5)
+        sg, so = g.state_by_id(6), o.state_by_id(6)
         assert np.array_equal(sg["block"], so["block"])
     assert o.num_particles == 3 and len(o.get_bonds()) == 2
 
@@ -375,17 +377,22 @@ def test_full_size_properties_and_window_parity(n):
     s = g.state_by_id(n)
     assert np.array_equal(s["block"], _numpy_find_block(sc.pos, geo["grid"], geo["dims"]))
     assert g.num_particles == n
-    # (2) Newton's third law: pair and bond forces cancel in the sum; what is left is gravity on
-    # the non-frozen particles (no particle starts within wall range)
-    f = g.eval_forces(1, n).astype(np.float64)
+    # (2) frozen particles feel nothing but still push: everyone else's force is bit-identical
+    # with and without the frozen set; and with nothing frozen Newton's third law holds: pair
+    # and bond forces cancel pairwise (each contribution is the exact negative of its twin), so
+    # the total is gravity alone (no particle starts within wall range)
+    f = g.eval_forces(1, n)
     frozen = np.zeros(n, bool)
     frozen[sc.frozen] = True
     assert np.all(f[frozen] == 0)
-    total = f.sum(0)
-    expect = np.array([0.0, -0.4 * float((~frozen).sum())])
-    # frozen particles still push their neighbours, so the balance is exact only up to the
-    # forces that frozen particles would have received
-    assert abs(total[0]) < 1e-6 * np.abs(f).sum() and abs(total[1] - expect[1]) < 1e-3 * abs(expect[1]) + 1e-6 * np.abs(f).sum()
+    g.set_frozen(np.zeros(0, np.int32))
+    f_free = g.eval_forces(1, n)
+    assert bits_equal(f[~frozen], f_free[~frozen])
+    g.set_frozen(sc.frozen)
+    total = f_free.astype(np.float64).sum(0)
+    mag = np.abs(f_free.astype(np.float64)).sum()
+    assert abs(total[0]) < 1e-6 * mag and abs(total[1] + 0.4 * n) < 1e-6 * mag + 1e-3 * 0.4 * n
+    f = f.astype(np.float64)
     # (3) window parity: interior forces depend only on particles within the bond reach
     rows, cols = sc.lattice
     c0 = sc.pos[(rows // 2) * cols + cols // 2]

@@ -182,6 +182,28 @@ int ptoy_id_capacity(ptoy_engine* h, size_t* n);
 /* blocks::FindBlock (blocks.h:155-163) evaluated on the device for n points; -1 = none. */
 int ptoy_find_blocks(ptoy_engine* h, const float* pos_xy, size_t n, int64_t* block);
 
+/* ---- strip decomposition across GPUs (new work: the reference is single-process) ---
+ *
+ * The domain is cut into strips over the slow block index (blocks.h:160: block = i*dims.j + j):
+ * rank r owns block columns [col_begin[r], col_begin[r+1]).  Per iteration the strips exchange
+ * their two boundary sub-rows before each force evaluation and the particles that crossed a
+ * strip boundary (or teleported) after the update.  N strips give bit-identical results to one
+ * GPU.  Configure BEFORE adding particles; ptoy_add_particles then keeps only the particles of
+ * the rank's own strip. */
+int ptoy_configure_strips(ptoy_engine* h, int rank, int world, const int32_t* col_begin /* world+1 */);
+/* One process per GPU: rank 0 creates the 128-byte id, every rank connects with it (collective). */
+int ptoy_nccl_unique_id(void* out128);
+int ptoy_nccl_connect(ptoy_engine* h, const void* uid128);
+/* Several strips in ONE process on ONE device (tests / development): the group steps them in
+ * lock step with device-to-device copies in place of NCCL.  Destroy the group before its engines. */
+typedef struct ptoy_group ptoy_group;
+int ptoy_group_create(ptoy_group** out, ptoy_engine** engines, int n);
+int ptoy_group_step_n(ptoy_group* g, int n);
+void ptoy_group_destroy(ptoy_group* g);
+/* Sticky device-side error bits: 2 arrivals exceed capacity, 4 ghost slice exceeds capacity,
+ * 8 a migrant outbox overflowed. */
+int ptoy_error_flags(ptoy_engine* h, int* flags);
+
 /* ---- measurement hooks -------------------------------------------------------------------- */
 
 /* Device time in ms of the kernels of the most recent ptoy_step_n(.., n), summed per

@@ -4,7 +4,9 @@
 ``libptoy_b200.so`` (include/ptoy_b200.h); ``scenes`` generates the synthetic workloads of
 BASELINE.json.  The package holds only what the hot path needs.
 """
-from .particles import Particles, PtoyError, load_library, LIB_PATH  # noqa: F401
+from .particles import (Particles, PtoyError, StripGroup, load_library, LIB_PATH,  # noqa: F401
+                        nccl_unique_id, partition_columns)
 from . import scenes  # noqa: F401
 
-__all__ = ["Particles", "PtoyError", "load_library", "LIB_PATH", "scenes"]
+__all__ = ["Particles", "PtoyError", "StripGroup", "load_library", "LIB_PATH", "scenes",
+           "nccl_unique_id", "partition_columns"]

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("PTOY_B200_LIB", os.path.join(HERE, "libptoy_b200.so"))
-SOURCES = ["kernels.cu", "engine.cu", "c_api.cu"]
+SOURCES = ["kernels.cu", "engine.cu", "dist.cu", "c_api.cu"]
 NVCC = os.environ.get("PTOY_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
         return LIB
     extra = os.environ.get("PTOY_NVCC_EXTRA", "").split()
     cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

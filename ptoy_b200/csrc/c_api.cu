@@ -3,6 +3,7 @@
 // its asserts become PTOY_ERR_ARG here).
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/ptoy_b200.h"
 #include "engine.h"
@@ -36,6 +37,17 @@ struct ptoy_engine {
     ptoy::set_last_error(err.what());                       \
     return PTOY_ERR_STATE;                                  \
   }
+
+namespace ptoy {
+struct LocalGroup;
+void nccl_unique_id(void* out128);
+LocalGroup* make_local_group(const std::vector<Engine*>& engines);
+void local_group_step(LocalGroup* g, int n);
+void local_group_destroy(LocalGroup* g);
+}  // namespace ptoy
+struct ptoy_group {
+  ptoy::LocalGroup* g;
+};
 
 extern "C" {
 
@@ -179,6 +191,53 @@ int ptoy_id_capacity(ptoy_engine* h, size_t* n) { PTOY_TRY(h, *n = E.id_capacity
 int ptoy_find_blocks(ptoy_engine* h, const float* pos, size_t n, int64_t* block) {
   PTOY_TRY(h, E.find_blocks(pos, n, block))
 }
+// ---- strip decomposition -----------------------------------------------------------------
+
+int ptoy_configure_strips(ptoy_engine* h, int rank, int world, const int32_t* col_begin) {
+  PTOY_TRY(h, E.configure_strips(rank, world, col_begin))
+}
+int ptoy_nccl_unique_id(void* out128) {
+  try {
+    ptoy::nccl_unique_id(out128);
+    return PTOY_OK;
+  } catch (const ptoy::Error& err) {
+    ptoy::set_last_error(err.what());
+    return err.code;
+  }
+}
+int ptoy_nccl_connect(ptoy_engine* h, const void* uid128) { PTOY_TRY(h, E.connect_nccl(uid128)) }
+int ptoy_group_create(ptoy_group** out, ptoy_engine** engines, int n) {
+  if (!out || !engines || n < 1) { ptoy::set_last_error("bad group arguments"); return PTOY_ERR_ARG; }
+  try {
+    std::vector<Engine*> v;
+    for (int i = 0; i < n; ++i) v.push_back(engines[i]->e);
+    *out = new ptoy_group{ptoy::make_local_group(v)};
+    return PTOY_OK;
+  } catch (const ptoy::Error& err) {
+    ptoy::set_last_error(err.what());
+    return err.code;
+  }
+}
+int ptoy_group_step_n(ptoy_group* g, int n) {
+  if (!g) { ptoy::set_last_error("null group"); return PTOY_ERR_ARG; }
+  try {
+    ptoy::local_group_step(g->g, n);
+    return PTOY_OK;
+  } catch (const ptoy::Error& err) {
+    ptoy::set_last_error(err.what());
+    return err.code;
+  } catch (const std::exception& err) {
+    ptoy::set_last_error(err.what());
+    return PTOY_ERR_STATE;
+  }
+}
+void ptoy_group_destroy(ptoy_group* g) {
+  if (!g) return;
+  ptoy::local_group_destroy(g->g);
+  delete g;
+}
+int ptoy_error_flags(ptoy_engine* h, int* flags) { PTOY_TRY(h, *flags = E.error_flags()) }
+
 int ptoy_enable_kernel_timing(ptoy_engine* h, int enable) { PTOY_TRY(h, E.enable_kernel_timing(enable != 0)) }
 int ptoy_get_kernel_times(ptoy_engine* h, double* ms6, int64_t* l6) { PTOY_TRY(h, E.kernel_times(ms6, l6)) }
 int ptoy_launch_count(ptoy_engine* h, int64_t* n) { PTOY_TRY(h, *n = E.launch_count()) }

@@ -29,7 +29,31 @@ struct GridDev {
   float inv_hsx, inv_hsy;  // fl(2/bs): approximate sub-cell coordinate w~ = (x - A) * inv_hs
   float tol;       // |w~ - w| bound used by the division-free binning (kernels.cu cell_of_fast)
   float wmax;      // largest |w| for which tol holds
+  // Strip decomposition: this engine stores sub-rows [row0, row0 + SI) of the
+  // global padded sub-grid as local rows [0, SI); it OWNS local rows [own_lo, own_hi); the two
+  // local rows below / above hold nothing locally and are served from the neighbours' ghost
+  // slices.  A single-GPU engine is the case row0 = 0, own = [2, SI - 2): the global padding rows.
+  int row0;
+  int own_lo, own_hi;
 };
+
+constexpr int kMaxRanks = 16;
+// Where the strips begin, as global sub-rows: rank r owns rows [row_begin[r], row_begin[r+1]).
+struct DistDev {
+  int world, rank;
+  int row_begin[kMaxRanks + 1];
+  // migrant outbox: one fixed-size block per destination rank, laid out as
+  //   int count (16 B header) | float2 pos[cap] | float2 vel[cap] | int id[cap] | int tag[cap]
+  // tag = old slot of the migrant on this rank: makes the receiver's order deterministic
+  char* out_base;          // nullptr: particles of other strips are simply dropped
+  long long out_stride;
+  int out_cap;
+};
+__host__ __device__ inline long long mig_off_pos() { return 16; }
+__host__ __device__ inline long long mig_off_vel(int cap) { return 16 + 8ll * cap; }
+__host__ __device__ inline long long mig_off_id(int cap) { return 16 + 16ll * cap; }
+__host__ __device__ inline long long mig_off_tag(int cap) { return 16 + 20ll * cap; }
+__host__ __device__ inline long long mig_stride(int cap) { return 16 + 24ll * cap; }
 
 // Physics constants, computed on the host with the reference's own expression
 // types (particles.cpp:7-24) so the bit patterns agree.
@@ -76,6 +100,7 @@ struct PortalSide {
 
 struct Counters {
   int n_cur;        // particles alive (valid slots [0,n_cur))
+  int n_arrived;    // migrants appended behind them, waiting for the reorder
   int n_next;       // alive after the pending reorder
   int n_total;      // n_next + trash
   int removed_total;
@@ -99,6 +124,12 @@ struct StageArgs {
   const int* id;
   const unsigned* cell;  // packed sub-cell (Si << 16 | Sj) of every sorted particle
   const int* start;      // [ncell+2] exclusive prefix of sub-cell populations
+  // ghost slices of the left (0) / right (1) neighbour strip for this stage: positions of its two
+  // boundary sub-rows and the matching slice of its start[] (2*SJ+1 entries, absolute indices
+  // into ITS array; entry 0 is the index of the first ghost particle).  nullptr = no neighbour.
+  const float2* gpos[2];
+  const int* gstart[2];
+  DistDev dist;
   float margin;          // extra search margin in sub-cell units
   // frozen_ as a bitmask over ids
   const uint32_t* frozen_bits;
@@ -138,6 +169,8 @@ struct TailArgs {  // standalone teleport + key pass (resize iterations, add_par
   const int* pblk;
   const uint8_t* blk_flags;
   int do_teleport;
+  DistDev dist;
+  const int* id;
   int first;     // particles [first, n) are processed
   unsigned* newcell;
   int* cnt;
@@ -159,6 +192,37 @@ struct ReorderArgs {
   int* id_out;
   unsigned* cell_out;
   int* slot_of_id;   // optional
+  // stable order across strips: locals sort as (rank, old slot), arrivals carry the (source
+  // rank, old slot there) they had; equals the single-GPU stable order
+  int rank;
+  const unsigned long long* arr_vkey;   // [n_arrived]
+};
+
+struct ArrivalArgs {   // migrants received from every source rank -> appended behind the locals
+  GridDev g;
+  Counters* ctr;
+  int world, in_cap;
+  const char* in_base;      // [world] blocks in the outbox layout (DistDev)
+  long long in_stride;
+  float2* pos;
+  float2* vel;
+  int* id;
+  unsigned* newcell;
+  int* cnt;
+  unsigned long long* arr_vkey;
+  int cap;
+};
+
+struct GhostPackArgs {   // boundary rows -> contiguous staging buffers for the neighbours
+  const Counters* ctr;
+  const float2* X;
+  const int* start;
+  int SJ;
+  int row_lo[2];      // first local row of the slice sent to the left (0) / right (1) neighbour
+  int ghost_cap;
+  float2* out_pos[2];
+  int* out_start[2];  // 2*SJ+1 entries, rebased to 0; nullptr = positions only (same layout as before)
+  int* err;
 };
 
 // launchers (kernels.cu)
@@ -169,6 +233,8 @@ void launch_scan(const int* cnt, int* start, int n_items, int ncell, unsigned lo
 void launch_fill(const ReorderArgs& a, int n_bound, cudaStream_t s);
 void launch_gather(const ReorderArgs& a, int n_bound, cudaStream_t s);
 void launch_finalize(Counters* ctr, int* ticket, cudaStream_t s);
+void launch_arrivals(const ArrivalArgs& a, cudaStream_t s);
+void launch_ghost_pack(const GhostPackArgs& a, cudaStream_t s);
 void launch_find_blocks(const GridDev& g, const float2* pos, size_t n, long long* out, cudaStream_t s);
 void launch_state_by_id(const GridDev& g, const Counters* ctr, const float2* pos, const float2* vel,
                         const int* id, int n_bound, float2* pos_by_id, float2* vel_by_id,

@@ -1,0 +1,295 @@
+// Strip decomposition across GPUs (SURVEY.md §8e — new work, the reference is
+// single-process).
+//
+// The 2-D domain is cut into strips over the SLOW block index (x): a strip is a contiguous range
+// of block columns = of sub-rows = of sorted particles.  Each rank steps its own strip with the
+// same kernels; what crosses a strip boundary per iteration is
+//   * before stage 1: the neighbour's two boundary sub-rows at x0 (positions + the matching
+//     slice of its start[]), before stage 2 the same rows at x_half  -> "ghost slices", plain
+//     contiguous copies because a strip's boundary rows are contiguous in its sorted arrays;
+//   * after stage 2: particles whose new sub-row belongs to another strip (any strip after a
+//     portal teleport) -> fixed-size per-destination outbox blocks, appended behind the
+//     receiver's particles and merged by its reorder.  Migrants carry (source rank, old slot), so
+//     the receiver's stable sort reproduces the single-GPU order: N strips == 1 GPU bit for bit.
+// No host synchronisation inside an iteration: all message sizes are fixed capacities.
+//
+// Transports: LocalGroup (several strips in one process on one device: the test vehicle, also
+// how the logic was developed without N GPUs) and NcclTransport (one process per GPU).
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound at run time (see NcclApi)
+
+#include <algorithm>
+#include <cstring>
+
+#include "engine.h"
+
+namespace ptoy {
+
+// NCCL is bound with dlopen/dlsym instead of a link-time dependency: a process that also runs
+// PyTorch must end up with ONE libnccl.so.2 (PyTorch's bundled one, which is newer than the
+// system copy and which libtorch_cuda requires); dlopen by soname returns whichever is already
+// loaded, and single-GPU users never load NCCL at all.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  static NcclApi& get() {
+    static NcclApi api = load();
+    return api;
+  }
+  static NcclApi load() {
+    NcclApi a;
+    void* h = nullptr;
+    if (const char* p = std::getenv("PTOY_NCCL_LIB")) h = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) throw Error(-5, std::string("cannot load libnccl.so.2: ") + dlerror());
+    auto sym = [&](const char* n) {
+      void* s = dlsym(h, n);
+      if (!s) throw Error(-5, std::string("libnccl.so.2 lacks ") + n);
+      return s;
+    };
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+    a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
+    a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+    return a;
+  }
+};
+
+#define CUDA_CHECK(expr)                                                                  \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      throw Error(-1, std::string(#expr) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+#define NCCL_CHECK(expr)                                                                  \
+  do {                                                                                    \
+    ncclResult_t r_ = (expr);                                                             \
+    if (r_ != ncclSuccess)                                                                \
+      throw Error(-5, std::string(#expr) + ": " + NcclApi::get().GetErrorString(r_));                \
+  } while (0)
+
+void Engine::configure_strips(int rank, int world, const int* col_begin) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) throw Error(-2, "bad rank / world");
+  read_counters();
+  if (h_ctr_->n_cur != 0) throw Error(-3, "configure_strips must precede add_particles");
+  strip_.world = world;
+  strip_.rank = rank;
+  for (int r = 0; r <= world; ++r) strip_.col_begin[r] = col_begin ? col_begin[r] : 0;
+  if (world > 1) {
+    if (!col_begin || col_begin[0] != 0 || col_begin[world] != di_) throw Error(-2, "col_begin must run from 0 to dims.i");
+    for (int r = 0; r < world; ++r)
+      if (col_begin[r + 1] - col_begin[r] < 2) throw Error(-2, "a strip needs at least 2 block columns");
+  }
+  alloc_cells();
+  env_dirty_ = true;
+}
+
+void Engine::alloc_strip_buffers() {
+  StripState& s = strip_;
+  // two boundary sub-rows hold about 2*SJ*1.2 particles at dense packing; allow 8 per sub-cell
+  s.ghost_cap = std::max(4096, 2 * grid_.SJ * 8);
+  s.out_cap = 1 << 16;
+  if (const char* v = std::getenv("PTOY_MIGRANT_CAP")) s.out_cap = std::max(256, atoi(v));
+  const size_t nstart = 2 * (size_t)grid_.SJ + 1;
+  for (int sd = 0; sd < 2; ++sd) {
+    s.send_pos[sd].alloc(s.ghost_cap);
+    s.send_start[sd].alloc(nstart);
+    s.ghost_pos[sd].alloc(s.ghost_cap);
+    s.ghost_pos_h[sd].alloc(s.ghost_cap);
+    s.ghost_start[sd].alloc(nstart);
+    CUDA_CHECK(cudaMemsetAsync(s.ghost_start[sd].p, 0, nstart * sizeof(int), stream_));
+    CUDA_CHECK(cudaMemsetAsync(s.send_start[sd].p, 0, nstart * sizeof(int), stream_));
+  }
+  const size_t bytes = (size_t)mig_stride(s.out_cap) * s.world;
+  s.outbox.alloc(bytes);
+  s.inbox.alloc(bytes);
+  CUDA_CHECK(cudaMemsetAsync(s.outbox.p, 0, bytes, stream_));
+  CUDA_CHECK(cudaMemsetAsync(s.inbox.p, 0, bytes, stream_));
+  s.arr_vkey.alloc((size_t)s.world * s.out_cap);
+}
+
+DistDev Engine::make_dist(bool with_outbox) const {
+  DistDev d{};
+  d.world = strip_.world;
+  d.rank = strip_.rank;
+  for (int r = 0; r <= strip_.world; ++r) d.row_begin[r] = strip_.row_begin[r];
+  d.out_cap = strip_.out_cap;
+  d.out_stride = mig_stride(strip_.out_cap);
+  d.out_base = (with_outbox && strip_.world > 1) ? reinterpret_cast<char*>(strip_.outbox.p) : nullptr;
+  return d;
+}
+
+void Engine::set_stream(cudaStream_t s) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (owns_stream_) cudaStreamDestroy(stream_);
+  stream_ = s;
+  owns_stream_ = false;
+}
+
+// Boundary rows -> staging buffers.  stage 1: positions at x0 + start[] slice; 2: x_half only.
+void Engine::phase_pack_halo(int stage) {
+  if (strip_.world == 1) return;
+  GhostPackArgs g{};
+  g.ctr = ctr_.p;
+  g.X = stage == 1 ? pos_[cur_].p : pos_h_.p;
+  g.start = start_.p;
+  g.SJ = grid_.SJ;
+  g.row_lo[0] = grid_.own_lo;
+  g.row_lo[1] = grid_.own_hi - 2;
+  g.ghost_cap = strip_.ghost_cap;
+  for (int sd = 0; sd < 2; ++sd) {
+    g.out_pos[sd] = strip_.send_pos[sd].p;
+    g.out_start[sd] = stage == 1 ? strip_.send_start[sd].p : nullptr;
+  }
+  g.err = &ctr_.p->err_flags;
+  if (cap_ == 0) return;
+  begin_timed(5);
+  launch_ghost_pack(g, stream_);
+  end_timed();
+}
+
+// ---------------------------------------------------------------------------------------------
+// In-process group of strips on one device (shared stream => phases are naturally ordered).
+// ---------------------------------------------------------------------------------------------
+struct LocalGroup : Transport {
+  std::vector<Engine*> e;
+  cudaStream_t stream = nullptr;
+
+  explicit LocalGroup(const std::vector<Engine*>& engines) : e(engines) {
+    if (e.empty()) throw Error(-2, "empty group");
+    CUDA_CHECK(cudaSetDevice(e[0]->device()));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (size_t r = 0; r < e.size(); ++r) {
+      if (e[r]->strip().world != (int)e.size() || e[r]->strip().rank != (int)r)
+        throw Error(-2, "group engines must be configured as ranks 0..n-1 of an n-strip decomposition");
+      if (e[r]->device() != e[0]->device()) throw Error(-2, "a local group lives on one device");
+      e[r]->set_stream(stream);
+      e[r]->set_transport(nullptr);  // the group drives the phases itself
+    }
+  }
+  ~LocalGroup() override {
+    if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream));
+  }
+  void halo_all(int stage) {
+    const int n = (int)e.size();
+    for (int r = 0; r < n; ++r) {
+      StripState& me = e[r]->strip_mut();
+      const size_t pb = (size_t)me.ghost_cap * sizeof(float2), sb = me.send_start[0].n * sizeof(int);
+      if (r > 0) {  // my first rows -> left neighbour's right ghost
+        StripState& l = e[r - 1]->strip_mut();
+        copy(stage == 1 ? l.ghost_pos[1].p : l.ghost_pos_h[1].p, me.send_pos[0].p, pb);
+        if (stage == 1) copy(l.ghost_start[1].p, me.send_start[0].p, sb);
+      }
+      if (r + 1 < n) {  // my last rows -> right neighbour's left ghost
+        StripState& rr = e[r + 1]->strip_mut();
+        copy(stage == 1 ? rr.ghost_pos[0].p : rr.ghost_pos_h[0].p, me.send_pos[1].p, pb);
+        if (stage == 1) copy(rr.ghost_start[0].p, me.send_start[1].p, sb);
+      }
+    }
+  }
+  void migrants_all() {
+    const int n = (int)e.size();
+    for (int s = 0; s < n; ++s)
+      for (int d = 0; d < n; ++d) {
+        if (s == d) continue;
+        const size_t st = (size_t)mig_stride(e[s]->strip().out_cap);
+        copy(e[d]->strip_mut().inbox.p + s * st, e[s]->strip_mut().outbox.p + d * st, st);
+      }
+  }
+  void halo(Engine&, int) override {}
+  void migrants(Engine&) override {}
+
+  void step_n(int iters) {
+    for (int it = 0; it < iters; ++it) {
+      for (auto* x : e) x->phase_prepare();
+      for (auto* x : e) x->phase_pack_halo(1);
+      halo_all(1);
+      for (auto* x : e) x->phase_stage1();
+      for (auto* x : e) x->phase_pack_halo(2);
+      halo_all(2);
+      for (auto* x : e) x->phase_stage2();
+      migrants_all();
+      for (auto* x : e) x->phase_reorder();
+      for (auto* x : e) x->phase_end();
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// One process per GPU: NCCL point-to-point over NVLink / NVSwitch on the engine's stream.
+// ---------------------------------------------------------------------------------------------
+struct NcclTransport : Transport {
+  ncclComm_t comm = nullptr;
+  explicit NcclTransport(Engine& e, const ncclUniqueId& id) {
+    CUDA_CHECK(cudaSetDevice(e.device()));
+    NCCL_CHECK(NcclApi::get().CommInitRank(&comm, e.strip().world, id, e.strip().rank));
+  }
+  ~NcclTransport() override {
+    if (comm) NcclApi::get().CommDestroy(comm);
+  }
+  void halo(Engine& e, int stage) override {
+    StripState& s = e.strip_mut();
+    const size_t pb = (size_t)s.ghost_cap * sizeof(float2), sb = s.send_start[0].n * sizeof(int);
+    NCCL_CHECK(NcclApi::get().GroupStart());
+    for (int sd = 0; sd < 2; ++sd) {
+      const int peer = sd == 0 ? s.rank - 1 : s.rank + 1;
+      if (peer < 0 || peer >= s.world) continue;
+      // my boundary rows on side sd become the peer's ghost on its opposite side; symmetric recv
+      NCCL_CHECK(NcclApi::get().Send(s.send_pos[sd].p, pb, ncclChar, peer, comm, e.stream()));
+      NCCL_CHECK(NcclApi::get().Recv(stage == 1 ? s.ghost_pos[sd].p : s.ghost_pos_h[sd].p, pb, ncclChar, peer, comm, e.stream()));
+      if (stage == 1) {
+        NCCL_CHECK(NcclApi::get().Send(s.send_start[sd].p, sb, ncclChar, peer, comm, e.stream()));
+        NCCL_CHECK(NcclApi::get().Recv(s.ghost_start[sd].p, sb, ncclChar, peer, comm, e.stream()));
+      }
+    }
+    NCCL_CHECK(NcclApi::get().GroupEnd());
+  }
+  void migrants(Engine& e) override {
+    StripState& s = e.strip_mut();
+    const size_t st = (size_t)mig_stride(s.out_cap);
+    NCCL_CHECK(NcclApi::get().GroupStart());
+    for (int r = 0; r < s.world; ++r) {
+      if (r == s.rank) continue;
+      NCCL_CHECK(NcclApi::get().Send(s.outbox.p + r * st, st, ncclChar, r, comm, e.stream()));
+      NCCL_CHECK(NcclApi::get().Recv(s.inbox.p + r * st, st, ncclChar, r, comm, e.stream()));
+    }
+    NCCL_CHECK(NcclApi::get().GroupEnd());
+  }
+};
+
+void Engine::delete_transport() {
+  delete transport_;
+  transport_ = nullptr;
+}
+void Engine::connect_nccl(const void* uid128) {
+  if (strip_.world < 2) throw Error(-3, "configure_strips first");
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(&id, uid128, sizeof(id));
+  set_transport(new NcclTransport(*this, id));
+}
+void nccl_unique_id(void* out128) {
+  ncclUniqueId id;
+  NCCL_CHECK(NcclApi::get().GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
+}
+LocalGroup* make_local_group(const std::vector<Engine*>& engines) { return new LocalGroup(engines); }
+void local_group_step(LocalGroup* g, int n) { g->step_n(n); }
+void local_group_destroy(LocalGroup* g) { delete g; }
+
+}  // namespace ptoy

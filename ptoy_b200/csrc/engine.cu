@@ -123,11 +123,12 @@ Engine::Engine(int device) : device_(device) {
 
 Engine::~Engine() {
   cudaSetDevice(device_);
-  if (stream_) cudaStreamSynchronize(stream_);
+  if (owns_stream_ && stream_) cudaStreamSynchronize(stream_); else cudaDeviceSynchronize();
   for (auto& tl : timed_) { cudaEventDestroy(tl.a); cudaEventDestroy(tl.b); }
   for (auto ev : event_pool_) cudaEventDestroy(ev);
   if (h_ctr_) cudaFreeHost(h_ctr_);
-  if (stream_) cudaStreamDestroy(stream_);
+  delete transport_;
+  if (stream_ && owns_stream_) cudaStreamDestroy(stream_);
 }
 
 // blocks::InitEmptyBlocks (blocks.h:256-276); particles are re-keyed by the caller
@@ -157,19 +158,33 @@ bool Engine::grown_grid(V2 pA, V2 pB, V2* nA, V2* nB) const {
 }
 
 void Engine::alloc_cells() {
-  const long long SI = 2ll * di_ + 6, SJ = 2ll * dj_ + 6;
+  const long long SIg = 2ll * di_ + 6, SJ = 2ll * dj_ + 6;
+  // strip decomposition: global sub-rows owned by this rank; one rank owns all
+  // rows between the global padding rows
+  if (strip_.world == 1) { strip_.row_begin[0] = 2; strip_.row_begin[1] = (int)SIg - 2; }
+  else {
+    for (int r = 0; r <= strip_.world; ++r)
+      strip_.row_begin[r] = r == 0 ? 2 : (r == strip_.world ? (int)SIg - 2 : 2 * strip_.col_begin[r] + 4);
+    for (int r = 0; r < strip_.world; ++r)
+      if (strip_.row_begin[r + 1] - strip_.row_begin[r] < 4) throw Error(-2, "a strip needs at least 2 block columns");
+  }
+  const int own_rows = strip_.row_begin[strip_.rank + 1] - strip_.row_begin[strip_.rank];
+  const long long SI = own_rows + 4;  // + two ghost rows on either side
   const long long ncell = SI * SJ;
   if (ncell + 8 >= (1ll << 31)) throw Error(-4, "sub-cell grid exceeds 2^31 cells");
-  if (SI > 65535 || SJ > 65535) throw Error(-4, "block grid exceeds 32764 blocks per axis");
+  if (SIg > 65535 || SJ > 65535) throw Error(-4, "block grid exceeds 32764 blocks per axis");
   grid_.Ax = gA_.x; grid_.Ay = gA_.y;
   grid_.bsx = bs_.x; grid_.bsy = bs_.y;
   grid_.di = di_; grid_.dj = dj_;
   grid_.fdi = (float)di_; grid_.fdj = (float)dj_;
   grid_.SI = (int)SI; grid_.SJ = (int)SJ;
   grid_.ncell = (int)ncell;
+  grid_.row0 = strip_.row_begin[strip_.rank] - 2;
+  grid_.own_lo = 2;
+  grid_.own_hi = (int)SI - 2;
   grid_.inv_hsx = 2.0f / bs_.x;
   grid_.inv_hsy = 2.0f / bs_.y;
-  grid_.wmax = (float)std::max(SI, SJ) + 8.f;
+  grid_.wmax = (float)std::max(SIg, SJ) + 8.f;
   grid_.tol = grid_.wmax * std::ldexp(1.f, -21);  // >= 2 * |w| * 2^-22 for |w| < wmax
   n_items_ = (int)(((ncell + 2) + 3) / 4 * 4);
   cnt_.alloc((size_t)n_items_);
@@ -184,11 +199,12 @@ void Engine::alloc_cells() {
   }
   blk_flags_.alloc((size_t)di_ * dj_);
   // search margins in sub-cell units
-  const float W = (float)std::max(SI, SJ);
+  const float W = (float)std::max(SIg, SJ);
   margin1_ = std::ldexp(1.f, -19) + W * std::ldexp(1.f, -21) + grid_.tol;
   const float drift = kVelocityLimit * dt_ * 0.5f;
   margin2_ = margin1_ + 2.f * drift / (0.5f * bs_.x) * 1.001f + W * std::ldexp(1.f, -21);
   if (!(margin2_ < 0.5f)) throw Error(-2, "time step too large for the sub-cell search margin");
+  if (strip_.world > 1) alloc_strip_buffers();
 }
 
 void Engine::ensure_capacity(size_t n) {
@@ -583,6 +599,11 @@ void Engine::read_counters() {
   n_bound_ = h_ctr_->n_cur;
 }
 
+int Engine::error_flags() {
+  read_counters();
+  return h_ctr_->err_flags;
+}
+
 size_t Engine::num_particles() {
   read_counters();
   return (size_t)h_ctr_->n_cur;
@@ -596,7 +617,7 @@ void Engine::add_particles(const float* pos, const float* vel, const int32_t* id
   read_counters();
   const size_t n_old = (size_t)h_ctr_->n_cur;
   if (n_old + n >= (1ull << 31) - 1024) throw Error(-4, "more than 2^31 particles");
-  ensure_capacity(n_old + n);
+  ensure_capacity(n_old + n + (size_t)arrivals_bound());  // strips: room for migrants
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   CUDA_CHECK(cudaMemcpyAsync(pos_[cur_].p + n_old, pos, n * sizeof(float2), kind, stream_));
   CUDA_CHECK(cudaMemcpyAsync(vel_[cur_].p + n_old, vel, n * sizeof(float2), kind, stream_));
@@ -661,6 +682,12 @@ StageArgs Engine::make_stage_args(int stage) {
   a.pos_out = pos_[cur_].p; a.vel_out = vel_[cur_].p;
   a.id = id_[cur_].p;
   a.start = start_.p;
+  for (int sd = 0; sd < 2; ++sd) {
+    const bool have = strip_.world > 1 && (sd == 0 ? strip_.rank > 0 : strip_.rank + 1 < strip_.world);
+    a.gpos[sd] = have ? (stage == 1 ? strip_.ghost_pos[sd].p : strip_.ghost_pos_h[sd].p) : nullptr;
+    a.gstart[sd] = have ? strip_.ghost_start[sd].p : nullptr;
+  }
+  a.dist = make_dist(true);
   a.margin = (stage == 1) ? margin1_ : margin2_;
   a.has_frozen = !frozen_.empty();
   a.frozen_bits = frozen_bits_.p;
@@ -671,7 +698,7 @@ StageArgs Engine::make_stage_args(int stage) {
   a.n_sides = has_portal_tables_ ? (int)portals_.size() * 2 : 0;
   a.sides = sides_.p; a.pblk_ptr = pblk_ptr_.p; a.pblk = pblk_.p;
   a.blk_flags = has_portal_tables_ ? blk_flags_.p : nullptr;
-  a.need_id = a.has_frozen || a.has_bonds || pick_enabled_;
+  a.need_id = a.has_frozen || a.has_bonds || pick_enabled_ || strip_.world > 1;
   a.force_out = nullptr;
   a.newcell = newcell_.p; a.cnt = cnt_.p;
   a.cell = cell_[cur_].p;
@@ -735,14 +762,16 @@ void Engine::reorder() {
   r.order = order_.p;
   r.pos_in = pos_[cur_].p; r.vel_in = vel_[cur_].p; r.id_in = id_[cur_].p;
   r.pos_out = pos_[cur_ ^ 1].p; r.vel_out = vel_[cur_ ^ 1].p; r.id_out = id_[cur_ ^ 1].p;
+  r.rank = strip_.rank;
+  r.arr_vkey = strip_.arr_vkey.p;
   const bool keep_map = !bonds_.empty();
   r.slot_of_id = keep_map ? slot_of_id_.p : nullptr;
   if (!keep_map) slot_map_valid_ = false;
   begin_timed(3);
-  launch_fill(r, n_bound_, stream_);
+  launch_fill(r, n_bound_ + arrivals_bound(), stream_);
   end_timed();
   begin_timed(4);
-  launch_gather(r, n_bound_, stream_);
+  launch_gather(r, n_bound_ + arrivals_bound(), stream_);
   end_timed();
   begin_timed(5);
   launch_finalize(ctr_.p, ticket_.p, stream_);
@@ -760,6 +789,8 @@ void Engine::rekey_and_reorder(int first, bool teleport) {
   a.sides = sides_.p; a.pblk_ptr = pblk_ptr_.p; a.pblk = pblk_.p;
   a.blk_flags = has_portal_tables_ ? blk_flags_.p : nullptr;
   a.do_teleport = teleport && a.n_sides > 0;
+  a.dist = make_dist(false);   // (re)binning never routes: particles of other strips are dropped
+  a.id = id_[cur_].p;
   a.first = first;
   a.newcell = newcell_.p; a.cnt = cnt_.p;
   begin_timed(5);
@@ -768,46 +799,82 @@ void Engine::rekey_and_reorder(int first, bool teleport) {
   reorder();
 }
 
-// One pass of the while loop at particles.cpp:96-201.
-void Engine::iterate() {
+// One pass of the while loop at particles.cpp:96-201, as phases, so that the exchanges of the
+// strip decomposition (dist.cu) can run between them.
+void Engine::phase_prepare() {
+  CUDA_CHECK(cudaSetDevice(device_));
   sync_env();
   sync_bonds();
   sync_frozen();
-  if (!bonds_.empty()) ensure_slot_map();
-
-  const float t_half = (float)((double)t_ + 0.5 * (double)dt_);          // :126
+  if (!bonds_.empty()) {
+    if (strip_.world > 1) throw Error(-3, "bonds are not supported across strips yet (DESIGN.md §7)");
+    ensure_slot_map();
+  }
+  t_half_ = (float)((double)t_ + 0.5 * (double)dt_);                      // :126
   // The serial tail's resize decision (:157-175) depends on host state only, so it is
   // taken up front: if the block grid grows, portals are detected after the re-binning.
-  V2 nA = domA_, nB = domB_;
+  rs_nA_ = domA_; rs_nB_ = domB_;
   const float lim = 0.01f;
   auto limit = [&](float& cur, float target) { cur = minf_std(cur + lim, maxf_std(cur - lim, target)); };
-  limit(nA.x, rqA_.x); limit(nA.y, rqA_.y); limit(nB.x, rqB_.x); limit(nB.y, rqB_.y);
-  const bool gate = f2i_trunc(t_half / dt_) % (int)(0.01 / (double)dt_) == 0;  // :170
-  const bool resize_now = gate && !(veq(nA, domA_) && veq(nB, domB_));
-  V2 gnA, gnB;
-  const bool grid_changes = resize_now && grown_grid(nA, nB, &gnA, &gnB);
+  limit(rs_nA_.x, rqA_.x); limit(rs_nA_.y, rqA_.y); limit(rs_nB_.x, rqB_.x); limit(rs_nB_.y, rqB_.y);
+  const bool gate = f2i_trunc(t_half_ / dt_) % (int)(0.01 / (double)dt_) == 0;  // :170
+  resize_now_ = gate && !(veq(rs_nA_, domA_) && veq(rs_nB_, domB_));
+  grid_changes_ = resize_now_ && grown_grid(rs_nA_, rs_nB_, &rs_gA_, &rs_gB_);
+  if (grid_changes_ && strip_.world > 1) throw Error(-3, "the block grid cannot grow while strip-decomposed");
+}
 
-  if (n_bound_ > 0) {
-    StageArgs a1 = make_stage_args(1);
-    begin_timed(0);
-    launch_stage(1, a1, n_bound_, stream_);
-    end_timed();
-    StageArgs a2 = make_stage_args(2);
-    a2.do_tail = !grid_changes;
-    begin_timed(1);
-    launch_stage(2, a2, n_bound_, stream_);
-    end_timed();
+void Engine::phase_stage1() {
+  if (n_bound_ <= 0) return;
+  StageArgs a1 = make_stage_args(1);
+  begin_timed(0);
+  launch_stage(1, a1, n_bound_, stream_);
+  end_timed();
+}
+
+void Engine::phase_stage2() {
+  if (strip_.world > 1) {  // empty the migrant outbox headers
+    const size_t st = (size_t)mig_stride(strip_.out_cap);
+    for (int r = 0; r < strip_.world; ++r) CUDA_CHECK(cudaMemsetAsync(strip_.outbox.p + r * st, 0, 16, stream_));
   }
-  if (resize_now) {
-    domA_ = nA; domB_ = nB;                                               // SetDomain(new_domain)
-    if (grid_changes) init_grid(gnA, gnB);
-    reset_env_frame(nA, nB);                                              // :173
+  if (n_bound_ <= 0) return;
+  StageArgs a2 = make_stage_args(2);
+  a2.do_tail = !grid_changes_;
+  begin_timed(1);
+  launch_stage(2, a2, n_bound_, stream_);
+  end_timed();
+}
+
+void Engine::phase_reorder() {
+  if (resize_now_) {
+    domA_ = rs_nA_; domB_ = rs_nB_;                                       // SetDomain(new_domain)
+    if (grid_changes_) init_grid(rs_gA_, rs_gB_);
+    reset_env_frame(rs_nA_, rs_nB_);                                      // :173
     sync_env();
   }
-  if (n_bound_ > 0) {
-    if (grid_changes) rekey_and_reorder(0, true);                         // :177-179 on the new grid
+  if (strip_.world > 1) {  // migrants from the other strips join before the sort
+    ArrivalArgs ar{};
+    ar.g = grid_;
+    ar.ctr = ctr_.p;
+    ar.world = strip_.world;
+    ar.in_cap = strip_.out_cap;
+    ar.in_base = reinterpret_cast<const char*>(strip_.inbox.p);
+    ar.in_stride = mig_stride(strip_.out_cap);
+    ar.pos = pos_[cur_].p; ar.vel = vel_[cur_].p; ar.id = id_[cur_].p;
+    ar.newcell = newcell_.p; ar.cnt = cnt_.p;
+    ar.arr_vkey = strip_.arr_vkey.p;
+    ar.cap = (int)cap_;
+    begin_timed(5);
+    launch_arrivals(ar, stream_);
+    end_timed();
+  }
+  if (n_bound_ > 0 || strip_.world > 1) {
+    if (grid_changes_) rekey_and_reorder(0, true);                        // :177-179 on the new grid
     else reorder();                                                       // :179
   }
+  if (strip_.world > 1) n_bound_ = (int)std::min<size_t>(cap_, (size_t)n_bound_ + arrivals_bound());
+}
+
+void Engine::phase_end() {
   // CheckBonds (:180): dead partners are already skipped on the device (prune_bonds()).
   if (remove_last_portal_) {                                              // :182-187
     if (!portals_.empty()) { portals_.pop_back(); env_dirty_ = true; }
@@ -818,7 +885,18 @@ void Engine::iterate() {
     compute_no_rendering();
     renderer_ready_ = false;
   }
-  t_ = (float)((double)t_half + 0.5 * (double)dt_);                       // :199
+  t_ = (float)((double)t_half_ + 0.5 * (double)dt_);                      // :199
+}
+
+void Engine::iterate() {
+  phase_prepare();
+  if (transport_) { phase_pack_halo(1); transport_->halo(*this, 1); }
+  phase_stage1();
+  if (transport_) { phase_pack_halo(2); transport_->halo(*this, 2); }
+  phase_stage2();
+  if (transport_) transport_->migrants(*this);
+  phase_reorder();
+  phase_end();
 }
 
 void Engine::step_to(float time_target) {

@@ -38,6 +38,21 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
+// Strip decomposition state: which block columns this rank owns, the staging
+// buffers of the halo exchange and the migrant in/outboxes.
+struct StripState {
+  int world = 1, rank = 0;
+  int col_begin[kMaxRanks + 1] = {0};  // first block column (blocks::dims_.i index) of every rank
+  int row_begin[kMaxRanks + 1] = {0};  // the same as global sub-rows
+  int ghost_cap = 0, out_cap = 0;
+  DevBuf<float2> send_pos[2];          // my boundary rows for the left / right neighbour
+  DevBuf<int> send_start[2];
+  DevBuf<float2> ghost_pos[2], ghost_pos_h[2];  // neighbours' boundary rows: at x0 / at x_half
+  DevBuf<int> ghost_start[2];
+  DevBuf<unsigned char> outbox, inbox; // world blocks each (common.h DistDev layout)
+  DevBuf<unsigned long long> arr_vkey;
+};
+
 class Engine {
  public:
   explicit Engine(int device);
@@ -94,6 +109,24 @@ class Engine {
   void eval_forces(int stage, size_t id_cap, float* force);
   size_t id_capacity() const { return id_cap_; }
   void find_blocks(const float* pos, size_t n, int64_t* block);
+
+  // strip decomposition (dist.cu).  Phases of one iteration, so that a transport (in-process
+  // group of strips, or NCCL between processes) can run the exchanges between them.
+  void configure_strips(int rank, int world, const int* col_begin);
+  const StripState& strip() const { return strip_; }
+  StripState& strip_mut() { return strip_; }
+  void phase_prepare();        // host bookkeeping: dirty state -> device, resize decision
+  void phase_pack_halo(int stage);   // boundary rows -> send buffers (stage 1: x0 + start slice, 2: x_half)
+  void phase_stage1();
+  void phase_stage2();
+  void phase_reorder();        // arrivals + reorder
+  void phase_end();            // snapshot, time
+  void set_transport(struct Transport* t) { delete_transport(); transport_ = t; }
+  void delete_transport();
+  void connect_nccl(const void* uid128);
+  void set_stream(cudaStream_t s);
+  int device() const { return device_; }
+  int error_flags();
 
   // measurement
   void enable_kernel_timing(bool e);
@@ -182,6 +215,16 @@ class Engine {
   int64_t kind_launches_[6] = {0, 0, 0, 0, 0, 0};
   int64_t launches_ = 0;
 
+  StripState strip_;
+  struct Transport* transport_ = nullptr;
+  bool owns_stream_ = true;
+  float t_half_ = 0.f;
+  bool resize_now_ = false, grid_changes_ = false;
+  V2 rs_nA_{0, 0}, rs_nB_{0, 0}, rs_gA_{0, 0}, rs_gB_{0, 0};
+  void alloc_strip_buffers();
+  DistDev make_dist(bool with_outbox) const;
+  int arrivals_bound() const { return strip_.world > 1 ? strip_.world * strip_.out_cap : 0; }
+
   // ---- helpers --------------------------------------------------------------------------
   void init_grid(V2 A, V2 B);                 // blocks::InitEmptyBlocks
   bool grown_grid(V2 pA, V2 pB, V2* nA, V2* nB) const;  // blocks::SetDomain's loop
@@ -205,6 +248,15 @@ class Engine {
   void begin_timed(int kind);
   void end_timed();
   void drain_timed();
+};
+
+// Exchanges between the strips of one iteration.  halo(stage): send_pos (+ send_start when
+// stage == 1) of every rank -> ghost_pos / ghost_pos_h (+ ghost_start) of its neighbours;
+// migrants(): outbox block d of rank s -> inbox block s of rank d.
+struct Transport {
+  virtual ~Transport() {}
+  virtual void halo(Engine& e, int stage) = 0;
+  virtual void migrants(Engine& e) = 0;
 };
 
 void set_last_error(const std::string& m);

@@ -103,8 +103,14 @@ __device__ __forceinline__ int block_of_s(const GridDev& g, int Si, int Sj) {
 __device__ __forceinline__ int block_of(const GridDev& g, const Cell& c) { return block_of_s(g, c.Si, c.Sj); }
 // packed sub-cell of a particle: Si << 16 | Sj ; kTrashCell = left the grid
 constexpr unsigned kTrashCell = 0xffffffffu;
-__device__ __forceinline__ unsigned pack_cell(const Cell& c) {
-  return c.valid ? ((unsigned)c.Si << 16) | (unsigned)c.Sj : kTrashCell;
+// local packed cell of a particle this strip keeps; kTrashCell if it left the grid or belongs
+// to another strip (`migrant`)
+__device__ __forceinline__ unsigned pack_cell(const GridDev& g, const Cell& c, bool& migrant) {
+  migrant = false;
+  if (!c.valid) return kTrashCell;
+  const int lr = c.Si - g.row0;
+  if (lr < g.own_lo || lr >= g.own_hi) { migrant = true; return kTrashCell; }
+  return ((unsigned)lr << 16) | (unsigned)c.Sj;
 }
 __device__ __forceinline__ int key_of_packed(unsigned p, int SJ, int ncell) {
   return p == kTrashCell ? ncell : (int)(p >> 16) * SJ + (int)(p & 0xffffu);
@@ -325,22 +331,32 @@ __device__ __forceinline__ float2 particle_force(
         }
       }
     };
-    auto scan = [&](int q, int end) {
+    auto scan = [&](const float2* __restrict__ P, int q, int end) {
       for (; q + 1 < end; q += 2) {
-        const float2 p0 = __ldg(X + q), p1 = __ldg(X + q + 1);
+        const float2 p0 = __ldg(P + q), p1 = __ldg(P + q + 1);
         test(p0);
         test(p1);
       }
-      if (q < end) test(__ldg(X + q));
+      if (q < end) test(__ldg(P + q));
     };
     for (int R = r_lo; R <= r_hi; ++R) {
-      const int base = R * a.g.SJ;
-      const int beg = __ldg(a.start + base + c_lo), end = __ldg(a.start + base + c_hi + 1);
-      if (R == Si) {
-        scan(beg, slot);
-        scan(slot + 1, end);
+      if (R >= a.g.own_lo && R < a.g.own_hi) {
+        const int base = R * a.g.SJ;
+        const int beg = __ldg(a.start + base + c_lo), end = __ldg(a.start + base + c_hi + 1);
+        if (R == Si) {
+          scan(X, beg, slot);
+          scan(X, slot + 1, end);
+        } else {
+          scan(X, beg, end);
+        }
       } else {
-        scan(beg, end);
+        // a row of the neighbouring strip: its particles and cell offsets arrive as ghost slices
+        const int side = R >= a.g.own_hi;
+        const int* gs = a.gstart[side];
+        if (gs == nullptr) continue;
+        const int base = (R - (side ? a.g.own_hi : a.g.own_lo - 2)) * a.g.SJ;
+        const int g0 = __ldg(gs);
+        scan(a.gpos[side], __ldg(gs + base + c_lo) - g0, __ldg(gs + base + c_hi + 1) - g0);
       }
     }
     for (int k = 0; k < nq; ++k) eval_hit(ph, hq.dx[k][t], hq.dy[k][t], fx, fy);
@@ -424,7 +440,9 @@ __device__ __forceinline__ float2 particle_force(
       for (int l = lb; l < le; ++l) {
         int r0, r1, c0, c1;
         block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
-        for (int R = r0; R <= r1; ++R) {
+        for (int Rg = r0; Rg <= r1; ++Rg) {
+          const int R = Rg - a.g.row0;  // strips: only locally stored rows (DESIGN.md §7 limitation)
+          if (R < a.g.own_lo || R >= a.g.own_hi) continue;
           const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
           for (int q = beg; q < end; ++q) {
             const float2 nb = X[q];
@@ -449,7 +467,9 @@ __device__ __forceinline__ float2 particle_force(
       for (int l = ob; l < oe; ++l) {
         int r0, r1, c0, c1;
         block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
-        for (int R = r0; R <= r1; ++R) {
+        for (int Rg = r0; Rg <= r1; ++Rg) {
+          const int R = Rg - a.g.row0;  // strips: only locally stored rows (DESIGN.md §7 limitation)
+          if (R < a.g.own_lo || R >= a.g.own_hi) continue;
           const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
           for (int q = beg; q < end; ++q) {
             const float2 nb = X[q];
@@ -526,8 +546,27 @@ __device__ __forceinline__ void teleport(const A& a, int blk, float2& x, float2&
   }
 }
 
-__device__ __forceinline__ void key_and_count(const GridDev& g, float2 x, int slot, unsigned* newcell, int* cnt) {
-  const unsigned pc = pack_cell(cell_of_fast(g, x));
+// New sub-cell of a particle after the update + histogram (the device half of
+// blocks::SortParticles).  A particle whose new sub-row belongs to another strip is put into
+// that strip's outbox (with its old slot, which fixes its place in the receiver's stable order)
+// and leaves this strip through the trash bin.
+__device__ __forceinline__ void key_and_count(const GridDev& g, const DistDev& d, float2 x, float2 v, int pid,
+                                              int slot, unsigned* newcell, int* cnt) {
+  const Cell c = cell_of_fast(g, x);
+  bool migrant;
+  const unsigned pc = pack_cell(g, c, migrant);
+  if (migrant && d.out_base) {
+    int dest = 0;
+    while (dest + 1 < d.world && c.Si >= d.row_begin[dest + 1]) ++dest;
+    char* blk = d.out_base + dest * d.out_stride;
+    const int k = atomicAdd(reinterpret_cast<int*>(blk), 1);
+    if (k < d.out_cap) {
+      reinterpret_cast<float2*>(blk + mig_off_pos())[k] = x;
+      reinterpret_cast<float2*>(blk + mig_off_vel(d.out_cap))[k] = v;
+      reinterpret_cast<int*>(blk + mig_off_id(d.out_cap))[k] = pid;
+      reinterpret_cast<int*>(blk + mig_off_tag(d.out_cap))[k] = slot;
+    }
+  }
   newcell[slot] = pc;
   atomicAdd(cnt + key_of_packed(pc, g.SJ, g.ncell), 1);  // result unused -> RED.ADD
 }
@@ -546,11 +585,11 @@ __global__ void __launch_bounds__(kThreads, PTOY_STAGE_MINB) stage_kernel(const 
   // fractional position inside it (only compared against the search margin)
   const unsigned pc = a.cell[i];
   const int Si = (int)(pc >> 16), Sj = (int)(pc & 0xffffu);
-  const float ui = fsub(x0.x, a.g.Ax) * a.g.inv_hsx - (float)(Si - 4);
+  const float ui = fsub(x0.x, a.g.Ax) * a.g.inv_hsx - (float)(Si + a.g.row0 - 4);
   const float uj = fsub(x0.y, a.g.Ay) * a.g.inv_hsy - (float)(Sj - 4);
   int blk = 0;
   unsigned flags = 0u;
-  if (a.blk_flags) { blk = block_of_s(a.g, Si, Sj); flags = a.blk_flags[blk]; }
+  if (a.blk_flags) { blk = block_of_s(a.g, Si + a.g.row0, Sj); flags = a.blk_flags[blk]; }
   const int pid = a.need_id ? a.id[i] : 0;
 
   float2 f = particle_force<STAGE>(a, X, hq, i, pid, x, v, Si, Sj, ui, uj, blk, flags);
@@ -582,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, PTOY_STAGE_MINB) stage_kernel(const 
     float2 vn = make_float2(vx, vy);
     if (a.do_tail) {
       if (flags & 1u) teleport(a, blk, xn, vn);
-      key_and_count(a.g, xn, i, a.newcell, a.cnt);
+      key_and_count(a.g, a.dist, xn, vn, pid, i, a.newcell, a.cnt);
     }
     a.pos_out[i] = xn;
     a.vel_out[i] = vn;
@@ -605,7 +644,7 @@ __global__ void __launch_bounds__(kThreads) tail_kernel(const __grid_constant__ 
       a.vel[i] = v;
     }
   }
-  key_and_count(a.g, x, i, a.newcell, a.cnt);
+  key_and_count(a.g, a.dist, x, a.vel[i], a.id[i], i, a.newcell, a.cnt);
 }
 
 // ---------------------------------------------------------------------------------
@@ -705,7 +744,7 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) fill_kernel(const __grid_constant__ ReorderArgs a) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
-  if (i >= a.ctr->n_cur) return;
+  if (i >= a.ctr->n_cur + a.ctr->n_arrived) return;
   const int key = key_of_packed(a.newcell[i], a.SJ, a.ncell);
   // counting down leaves the histogram all-zero again for the next iteration
   const int r = atomicSub(a.cnt + key, 1) - 1;
@@ -728,10 +767,15 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const __grid_constant_
   const int beg = a.start[c], end = a.start[c + 1];
   if (end - beg > 1) {
     const int want = k - beg;
+    const int n_loc = a.ctr->n_cur;
+    auto vkey = [&](int i) -> unsigned long long {
+      return i < n_loc ? ((unsigned long long)a.rank << 32) | (unsigned)i : a.arr_vkey[i - n_loc];
+    };
     for (int e = beg; e < end; ++e) {
       const int cand = a.order[e];
+      const unsigned long long ck = vkey(cand);
       int smaller = 0;
-      for (int e2 = beg; e2 < end; ++e2) smaller += (a.order[e2] < cand);
+      for (int e2 = beg; e2 < end; ++e2) smaller += (vkey(a.order[e2]) < ck);
       if (smaller == want) { src = cand; break; }
     }
   }
@@ -746,7 +790,53 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const __grid_constant_
 __global__ void finalize_kernel(Counters* ctr, int* ticket) {
   ctr->removed_total += ctr->n_total - ctr->n_next;
   ctr->n_cur = ctr->n_next;
+  ctr->n_arrived = 0;
   *ticket = 0;
+}
+
+// Migrants received from the other strips are appended behind the local particles, keyed and
+// counted, ready for the reorder; their (source rank, old slot) tags become their sort keys.
+__global__ void __launch_bounds__(kThreads) arrivals_kernel(const __grid_constant__ ArrivalArgs a) {
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  const int src = t / a.in_cap, k = t - src * a.in_cap;
+  if (src >= a.world) return;
+  int off = 0, total = 0, mine = 0;
+  for (int r = 0; r < a.world; ++r) {
+    const int raw = *reinterpret_cast<const int*>(a.in_base + r * a.in_stride);
+    if (raw > a.in_cap && t == 0) atomicOr(&a.ctr->err_flags, 8);  // a sender's outbox overflowed
+    const int c = min(raw, a.in_cap);
+    if (r < src) off += c;
+    if (r == src) mine = c;
+    total += c;
+  }
+  if (t == 0) a.ctr->n_arrived = total;
+  if (k >= mine) return;
+  const int n_loc = a.ctr->n_cur;
+  const int dst = n_loc + off + k;
+  if (dst >= a.cap) { atomicOr(&a.ctr->err_flags, 2); return; }
+  const char* blk = a.in_base + src * a.in_stride;
+  const float2 x = reinterpret_cast<const float2*>(blk + mig_off_pos())[k];
+  a.pos[dst] = x;
+  a.vel[dst] = reinterpret_cast<const float2*>(blk + mig_off_vel(a.in_cap))[k];
+  a.id[dst] = reinterpret_cast<const int*>(blk + mig_off_id(a.in_cap))[k];
+  a.arr_vkey[off + k] = ((unsigned long long)src << 32) |
+                        (unsigned)reinterpret_cast<const int*>(blk + mig_off_tag(a.in_cap))[k];
+  bool migrant;
+  const unsigned pc = pack_cell(a.g, cell_of_fast(a.g, x), migrant);  // the sender routed it here
+  a.newcell[dst] = pc;
+  atomicAdd(a.cnt + key_of_packed(pc, a.g.SJ, a.g.ncell), 1);
+}
+
+// Copy the two boundary sub-rows on each side into staging buffers (positions; optionally the
+// matching slice of start[], rebased to 0) for the neighbouring strips.
+__global__ void __launch_bounds__(kThreads) ghost_pack_kernel(const __grid_constant__ GhostPackArgs a) {
+  const int side = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  const int c0 = a.row_lo[side] * a.SJ;
+  const int b0 = a.start[c0], b1 = a.start[c0 + 2 * a.SJ];
+  if (t == 0 && b1 - b0 > a.ghost_cap) atomicOr(a.err, 4);
+  if (t < b1 - b0 && t < a.ghost_cap) a.out_pos[side][t] = a.X[b0 + t];
+  if (a.out_start[side] && t <= 2 * a.SJ) a.out_start[side][t] = a.start[c0 + t] - b0;
 }
 
 // ---------------------------------------------------------------------------------
@@ -831,6 +921,13 @@ void launch_fill(const ReorderArgs& a, int n_bound, cudaStream_t s) {
 void launch_gather(const ReorderArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound <= 0) return;
   gather_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(a);
+}
+void launch_arrivals(const ArrivalArgs& a, cudaStream_t s) {
+  arrivals_kernel<<<grid_for((size_t)a.world * a.in_cap), kThreads, 0, s>>>(a);
+}
+void launch_ghost_pack(const GhostPackArgs& a, cudaStream_t s) {
+  const size_t n = (size_t)max(a.ghost_cap, 2 * a.SJ + 1);
+  ghost_pack_kernel<<<dim3(grid_for(n), 2), kThreads, 0, s>>>(a);
 }
 void launch_finalize(Counters* ctr, int* ticket, cudaStream_t s) {
   finalize_kernel<<<1, 1, 0, s>>>(ctr, ticket);

@@ -2,9 +2,9 @@
 // doing what main.cpp / ptoy_wasm.cpp / control.cpp do: per frame
 // SetRendererReadyForNext(true); step(GetTime() + dt); read the getters — plus a scripted UI
 // session (gravity, point force, bonds, freeze, portals, resize).  The SAME source is linked once
-// against the reference's particles.cpp (oracle/_ref/drop_in_driver_ref) and once against the
-// drop-in facade + libptoy_b200.so (ptoy_b200/host/drop_in_driver_b200); tests/test_dropin_gpu.py
-// compares their outputs.
+// against the reference's particles.cpp (test infrastructure, see the Makefile) and once against
+// the drop-in facade + libptoy_b200.so (drop_in_driver_b200); tests/test_dropin_gpu.py compares
+// their outputs.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>

@@ -215,6 +215,7 @@ void Particles::step(Scal time_target, bool quit) {  // particles.cpp:93-203
   if (quit) return;
   ptoy_engine* e = engine_of(this);
   sync_inline_state(this, e);
+  const RectVect domain_before = domain;
   const bool snap = renderer_ready_for_next_;
   check(ptoy_set_renderer_ready(e, snap), "renderer_ready");
   float before = 0, after = 0;
@@ -234,7 +235,8 @@ void Particles::step(Scal time_target, bool quit) {  // particles.cpp:93-203
     check(ptoy_get_domain(e, dom), "domain");
     domain = RectVect(Vect(dom[0], dom[1]), Vect(dom[2], dom[3]));
   }
-  if (remove_last_portal_) {  // :182-187 happened inside the engine
+  if (remove_last_portal_ || domain != domain_before) {
+    // :182-187 happened inside the engine / the frame moved: UpdateEnvObj re-derived Portal::blocks
     remove_last_portal_ = false;
     pull_portals(this, e);
   }

@@ -77,13 +77,17 @@ SIGNATURES = {
     "ptoy_eval_forces": [_i, _sz, _f32p],
     "ptoy_id_capacity": [_szp],
     "ptoy_find_blocks": [_f32p, _sz, _i64p],
+    "ptoy_configure_strips": [_i, _i, _i32p],
+    "ptoy_nccl_connect": [_vp],
+    "ptoy_error_flags": [_ip],
     "ptoy_enable_kernel_timing": [_i],
     "ptoy_get_kernel_times": [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), _i64p],
     "ptoy_launch_count": [C.POINTER(C.c_int64)],
     "ptoy_stream": [C.POINTER(C.c_void_p)],
 }
 # entry points that do not take a handle first
-FREE_FUNCTIONS = ["ptoy_last_error", "ptoy_abi_version", "ptoy_create", "ptoy_destroy"]
+FREE_FUNCTIONS = ["ptoy_last_error", "ptoy_abi_version", "ptoy_create", "ptoy_destroy",
+                  "ptoy_nccl_unique_id", "ptoy_group_create", "ptoy_group_step_n", "ptoy_group_destroy"]
 KERNEL_KINDS = ["stage1", "stage2", "scan", "fill", "gather", "other"]
 
 TOOLS = {"bonds": 0, "pick": 1, "freeze": 2, "portal": 3}
@@ -113,6 +117,14 @@ def load_library():
     L.ptoy_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     L.ptoy_destroy.restype = None
     L.ptoy_destroy.argtypes = [C.c_void_p]
+    L.ptoy_nccl_unique_id.restype = C.c_int
+    L.ptoy_nccl_unique_id.argtypes = [C.c_void_p]
+    L.ptoy_group_create.restype = C.c_int
+    L.ptoy_group_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
+    L.ptoy_group_step_n.restype = C.c_int
+    L.ptoy_group_step_n.argtypes = [C.c_void_p, C.c_int]
+    L.ptoy_group_destroy.restype = None
+    L.ptoy_group_destroy.argtypes = [C.c_void_p]
     for name, args in SIGNATURES.items():
         fn = getattr(L, name)
         fn.restype = C.c_int
@@ -497,6 +509,29 @@ class Particles:
         self._call("ptoy_find_blocks", pos, len(pos), out)
         return out[:len(pos)]
 
+    # ------------------------------------------------------------------ strips (multi-GPU)
+    def configure_strips(self, rank, world, col_begin=None):
+        """Own block columns [col_begin[rank], col_begin[rank+1]) of the current grid.  Call after
+        reset_scene and before add_particles; add_particles then keeps only this strip's particles."""
+        if col_begin is None:
+            col_begin = partition_columns(self.geometry()["dims"][0], world)
+        cb = np.ascontiguousarray(col_begin, dtype=np.int32)
+        assert len(cb) == world + 1
+        self._call("ptoy_configure_strips", int(rank), int(world), cb)
+        self.rank, self.world, self.col_begin = int(rank), int(world), cb
+
+    def nccl_connect(self, uid):
+        """Collective: every rank passes the 128-byte id created by nccl_unique_id() on rank 0."""
+        _prefer_torch_nccl()
+        buf = (C.c_char * 128).from_buffer_copy(bytes(uid))
+        self._call("ptoy_nccl_connect", C.cast(buf, C.c_void_p))
+
+    @property
+    def error_flags(self):
+        f = C.c_int()
+        self._call("ptoy_error_flags", C.byref(f))
+        return f.value
+
     # ------------------------------------------------------------------ measurement
     def enable_kernel_timing(self, enable=True):
         self._call("ptoy_enable_kernel_timing", int(enable))
@@ -518,3 +553,113 @@ class Particles:
         s = C.c_void_p()
         self._call("ptoy_stream", C.byref(s))
         return s.value
+
+
+def partition_columns(n_columns, world, weights=None):
+    """Strip boundaries over the block columns: equal columns, or balanced by `weights` (particle
+    count per column).  Every strip gets at least two columns."""
+    if world == 1:
+        return np.array([0, n_columns], np.int32)
+    assert n_columns >= 2 * world, "each strip needs at least two block columns"
+    if weights is None:
+        cb = np.round(np.linspace(0, n_columns, world + 1)).astype(np.int64)
+    else:
+        w = np.asarray(weights, np.float64)
+        assert len(w) == n_columns
+        c = np.r_[0.0, np.cumsum(w)]
+        targets = c[-1] * np.arange(world + 1) / world
+        cb = np.searchsorted(c, targets, side="left").astype(np.int64)
+        cb[0], cb[-1] = 0, n_columns
+    for r in range(1, world):                      # enforce the two-column minimum
+        cb[r] = max(cb[r], cb[r - 1] + 2)
+    for r in range(world - 1, 0, -1):
+        cb[r] = min(cb[r], cb[r + 1] - 2)
+    return cb.astype(np.int32)
+
+
+def _prefer_torch_nccl():
+    """The engine binds NCCL by soname at run time; importing torch first makes that PyTorch's
+    bundled libnccl.so.2 (newer than the system copy, and the one libtorch_cuda needs)."""
+    try:
+        import torch  # noqa: F401
+    except Exception:
+        pass
+
+
+def nccl_unique_id():
+    _prefer_torch_nccl()
+    L = load_library()
+    buf = (C.c_char * 128)()
+    rc = L.ptoy_nccl_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise PtoyError(rc, L.ptoy_last_error().decode())
+    return bytes(buf)
+
+
+class StripGroup:
+    """Several strips of one scene in ONE process on ONE device, stepped in lock step with
+    device-to-device copies in place of NCCL (include/ptoy_b200.h ptoy_group_*).  The test
+    vehicle of the multi-GPU path: N virtual strips must equal one engine bit for bit."""
+
+    def __init__(self, domain, world, device=0, col_begin=None, gravity=(True, (0.0, -10.0))):
+        self.L = load_library()
+        self.parts = []
+        for r in range(world):
+            p = Particles(device=device, default_scene=False)
+            p.reset_scene(domain)
+            p.set_gravity(*gravity)
+            p.configure_strips(r, world, col_begin)
+            p.set_renderer_ready(False)
+            self.parts.append(p)
+        arr = (C.c_void_p * world)(*[p.h for p in self.parts])
+        g = C.c_void_p()
+        rc = self.L.ptoy_group_create(C.byref(g), arr, world)
+        if rc != 0:
+            raise PtoyError(rc, self.L.ptoy_last_error().decode())
+        self.g = g
+
+    def each(self, fn):
+        for p in self.parts:
+            fn(p)
+
+    def add_particles(self, pos, vel, ids):
+        self.each(lambda p: p.add_particles(pos, vel, ids))
+
+    def step_n(self, n):
+        rc = self.L.ptoy_group_step_n(self.g, int(n))
+        if rc != 0:
+            raise PtoyError(rc, self.L.ptoy_last_error().decode())
+
+    def state_by_id(self, cap):
+        """Union of the strips' states (every particle lives on exactly one strip)."""
+        out = None
+        owners = np.zeros(cap, np.int32)
+        for p in self.parts:
+            s = p.state_by_id(cap)
+            alive = s["block"] >= 0
+            owners += alive
+            if out is None:
+                out = {k: v.copy() for k, v in s.items()}
+            else:
+                for k in out:
+                    out[k][alive] = s[k][alive]
+        assert owners.max() <= 1, "a particle is held by two strips"
+        return out
+
+    @property
+    def num_particles(self):
+        return sum(p.num_particles for p in self.parts)
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.L.ptoy_group_destroy(self.g)
+            self.g = None
+        for p in self.parts:
+            p.close()
+        self.parts = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -135,6 +135,55 @@ def add_portals(scene, n_pairs, length=1.0, seed=7):
     return scene
 
 
+def strip_scene(n_per_rank, rank, world, pitch_over_r=2.2, jitter_over_r=0.025, seed=1234, aspect=None):
+    """Weak-scaling scene (configs[4]/[5] style dense packing): ONE global hex-packed scene of
+    world * n_per_rank particles whose width grows with `world`; returns the particles of the
+    block columns that `rank` owns under the equal-column partition, with global ids.
+
+    The x direction is the slow block index (blocks.h:160), i.e. the direction strips are cut in.
+    Attributes: n_global, col_begin (the partition to pass to configure_strips), dims."""
+    from .particles import partition_columns
+    r = float(R)
+    pitch = pitch_over_r * r
+    row_h = pitch * np.sqrt(3.0) / 2.0
+    # strip aspect: height fixed by one rank's share, width proportional to world
+    h1 = np.sqrt(n_per_rank * pitch * row_h * (aspect or 0.75))
+    rows = max(4, int(round(h1 / row_h)))
+    cols_per_rank = int(np.ceil(n_per_rank / rows))
+    cols = cols_per_rank * world
+    n_global = rows * cols
+    bx = -1.0 + 2 * r + pitch * (cols + 0.5)
+    by = -1.0 + 2 * r + row_h * rows + pitch
+    domain = (-1.0, -1.0, float(np.float32(bx)), float(np.float32(by)))
+    bs = float(BLOCK)
+    di = int(np.float32(np.float32(domain[2]) - np.float32(-1.0)) / BLOCK) + 1
+    dj = int(np.float32(np.float32(domain[3]) - np.float32(-1.0)) / BLOCK) + 1
+    cb = partition_columns(di, world)
+    # lattice columns that can fall into this rank's block columns (one extra on each side)
+    x_lo, x_hi = -1.0 + cb[rank] * bs, -1.0 + cb[rank + 1] * bs
+    i_lo = max(0, int(np.floor((x_lo + 1.0 - r) / pitch)) - 2)
+    i_hi = min(cols, int(np.ceil((x_hi + 1.0 - r) / pitch)) + 2)
+    ii, jj = np.meshgrid(np.arange(i_lo, i_hi, dtype=np.int64), np.arange(rows, dtype=np.int64))
+    ii, jj = ii.ravel(), jj.ravel()
+    ids = jj * cols + ii
+    x = -1.0 + r + pitch * (ii + 0.5 + 0.5 * (jj % 2))
+    y = -1.0 + r + pitch * 0.5 + row_h * jj
+    # jitter is a function of the GLOBAL id, so every rank generates the same particle
+    rng = np.random.RandomState(seed)
+    mult = np.uint64(0x9E3779B97F4A7C15)
+    hsh = (ids.astype(np.uint64) + np.uint64(seed)) * mult
+    jx = ((hsh >> np.uint64(11)) & np.uint64(0xFFFFF)).astype(np.float64) / float(0xFFFFF) * 2 - 1
+    jy = ((hsh >> np.uint64(33)) & np.uint64(0xFFFFF)).astype(np.float64) / float(0xFFFFF) * 2 - 1
+    pos = np.stack([x + jx * jitter_over_r * r, y + jy * jitter_over_r * r], 1).astype(np.float32)
+    # ownership exactly as the engine decides it: blocks::FindBlock column of the float32 position
+    col = np.trunc((pos[:, 0] - np.float32(-1.0)) / BLOCK).astype(np.int64)
+    mine = (col >= cb[rank]) & (col < cb[rank + 1])
+    sc = Scene(domain, pos[mine], np.zeros((int(mine.sum()), 2), np.float32), ids[mine].astype(np.int32),
+               name=f"strip{rank}of{world}x{n_per_rank}")
+    sc.n_global, sc.col_begin, sc.dims = int(n_global), cb, (di, dj)
+    return sc
+
+
 def config3(n=16_000_000, seed=1234):
     """BASELINE.json configs[2]: hex pitch 2.02r, jitter ±0.01r, ~4 directed bonds per
     particle, 1 % frozen."""

@@ -1,0 +1,107 @@
+"""Strip decomposition: N virtual strips on one device (in-process transport in
+place of NCCL) must reproduce the single engine BIT FOR BIT — halo exchange before both force
+evaluations, migration across strip boundaries, deterministic merge of the migrants."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+import ptoy_b200
+from ptoy_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def single(sc, steps, setup=None):
+    g = ptoy_b200.Particles(device=0, default_scene=False)
+    g.reset_scene(sc.domain)
+    g.set_gravity(*sc.gravity)
+    g.add_particles(sc.pos, sc.vel, sc.ids)
+    if setup:
+        setup(g)
+    g.set_renderer_ready(False)
+    g.step_n(steps)
+    return g.state_by_id(sc.n), g.num_particles
+
+
+def strips(sc, steps, world, col_begin=None, setup=None):
+    grp = ptoy_b200.StripGroup(sc.domain, world, col_begin=col_begin, gravity=sc.gravity)
+    grp.add_particles(sc.pos, sc.vel, sc.ids)
+    if setup:
+        grp.each(setup)
+    assert grp.num_particles == sc.n          # every particle is owned exactly once
+    grp.step_n(steps)
+    out = grp.state_by_id(sc.n), grp.num_particles
+    flags = [p.error_flags for p in grp.parts]
+    grp.close()
+    assert not any(flags), flags
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_strips_equal_single_engine_moving_particles(world):
+    # velocities up to 4: ~1 % of the particles change sub-row per step, so 60 steps push
+    # thousands across the strip boundaries in both directions
+    sc = scenes.hex_lattice(30000, 2.2, 0.025, seed=17, vel_scale=4.0)
+    ref, n_ref = single(sc, 60)
+    got, n_got = strips(sc, 60, world)
+    assert n_got == n_ref == sc.n
+    assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])
+    assert np.array_equal(got["block"], ref["block"])
+
+
+def test_strips_with_uneven_boundaries_and_overlapping_particles():
+    sc = scenes.uniform_random(40000, seed=5)
+    g = ptoy_b200.Particles(device=0, default_scene=False)
+    g.reset_scene(sc.domain)
+    di = g.geometry()["dims"][0]
+    cb = np.array([0, 2, di // 3, di - 2, di], np.int32)   # two minimal strips at the edges
+    ref, n_ref = single(sc, 8)
+    got, n_got = strips(sc, 8, 4, col_begin=cb)
+    assert n_got == n_ref
+    assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])
+
+
+def test_strips_with_frozen_point_force_and_removal():
+    sc = scenes.hex_lattice(12000, 2.2, 0.025, seed=9, vel_scale=2.0)
+    ax, ay, bx, by = sc.domain
+    # some particles start outside the right wall and fly out of the grid
+    extra = np.array([[bx + 0.03, ay + 0.5], [bx + 0.03, ay + 0.9]], np.float32)
+    sc.pos = np.concatenate([sc.pos, extra])
+    sc.vel = np.concatenate([sc.vel, np.array([[9, 0], [9, 0]], np.float32)])
+    sc.ids = np.arange(len(sc.pos), dtype=np.int32)
+    frozen = np.arange(0, 12000, 11, dtype=np.int32)
+
+    def setup(p):
+        p.set_frozen(frozen)
+        p.set_point_force(True, True, (ax + 1.0, ay + 0.6))
+    ref, n_ref = single(sc, 40, setup)
+    got, n_got = strips(sc, 40, 3, setup=setup)
+    assert n_got == n_ref == 12000
+    assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])
+
+
+def test_teleports_migrate_to_any_strip():
+    """A portal whose partner lives three strips away: teleported particles are routed to the
+    far strip by the same outbox mechanism.  (Cross-portal pair forces need both portals on one
+    strip — DESIGN.md §7 — so the portals sit in empty space here: the check is the routing.)"""
+    sc = scenes.hex_lattice(6000, 2.2, 0.025, seed=3, vel_scale=0.0)
+    ax, ay, bx, top = sc.domain
+    by = top + 1.0                         # head room above the packing for the beam and the portals
+    sc.domain = (ax, ay, bx, by)
+    # a beam of fast particles flying into the left portal
+    yb = by - 0.6 + np.linspace(0, 0.3, 40)
+    beam = np.stack([np.full(40, ax + 0.3), yb], 1).astype(np.float32)
+    sc.pos = np.concatenate([sc.pos, beam])
+    sc.vel = np.concatenate([sc.vel, np.tile(np.array([[8.0, 0.0]], np.float32), (40, 1))])
+    sc.ids = np.arange(len(sc.pos), dtype=np.int32)
+    sc.gravity = (False, (0.0, -10.0))
+    x0, x1 = ax + 0.5, bx - 0.5
+    portal = ((x0, by - 0.8), (x0, by - 0.1), (x1, by - 0.8), (x1, by - 0.1))
+
+    def setup(p):
+        p.add_portal_pair(*portal)
+    ref, _ = single(sc, 70, setup)
+    got, _ = strips(sc, 70, 4, setup=setup)
+    moved = ref["pos"][6000:, 0] > x1      # the beam came out of the far portal
+    assert moved.sum() >= 30
+    assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the particle-stepping hot path (BASELINE.json metric: particle-updates/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n PARTICLES]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--particles PER_GPU]
 
 One "step" = one iteration of the loop at particles.cpp:96-201 (two force evaluations + one
 re-binning) over the whole scene.  Workload at N=1: BASELINE.json configs[2] — 16M particles,
@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -73,9 +73,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,7 +85,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        where = "warm-up + timed region + per-kernel pass (all under load)"
+        if window is not None:
+            inside = [r for r in rows if window[0] <= r[0] <= window[1]]
+            if len(inside) >= 2:
+                rows, where = inside, "timed region"
+        for _, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -99,14 +105,8 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
-
-def strip_scene(n, rank, world):
-    """Rank-local scene: config3 geometry, ids offset so they are globally unique."""
-    from ptoy_b200 import scenes
-    sc = scenes.config3(n, seed=1234 + rank)
-    return sc
 
 
 def run_reference(args):
@@ -176,8 +176,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--n", type=int, default=16_000_000, help="particles per GPU")
-    ap.add_argument("--ref-n", type=int, default=1_000_000, help="particles of the bounded CPU sample")
+    ap.add_argument("--particles", dest="n", type=int, default=16_000_000, help="particles per GPU")
+    ap.add_argument("--ref-particles", dest="ref_n", type=int, default=1_000_000, help="particles of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bonds", action="store_true", help="pair/gravity/walls only (configs[1]-style)")
@@ -208,10 +208,30 @@ def main():
 
     # ---- scene ---------------------------------------------------------------------------
     t0 = time.time()
-    sc = scenes.hex_lattice(args.n, 2.02, 0.01, seed=1234 + rank) if args.no_bonds else strip_scene(args.n, rank, world)
-    n = sc.n
     g = ptoy_b200.Particles(device=local, default_scene=False)
-    scenes.load_into(g, sc)
+    if world == 1:
+        sc = scenes.hex_lattice(args.n, 2.02, 0.01) if args.no_bonds else scenes.config3(args.n)
+        scenes.load_into(g, sc)
+        workload = ("configs[2]: 16M particles, hex pitch 2.02r, ~4 directed bonds/particle, 1% frozen"
+                    if not args.no_bonds else "pair+gravity+walls only, hex pitch 2.02r")
+        parallelism = "1 GPU"
+    else:
+        # configs[4]-style dense packing, ONE global scene cut into strips over x (weak scaling:
+        # args.n particles per GPU); halo exchange + migration over NCCL every iteration
+        sc = scenes.strip_scene(args.n, rank, world)
+        g.reset_scene(sc.domain)
+        g.set_gravity(*sc.gravity)
+        g.configure_strips(rank, world, sc.col_begin)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ptoy_b200.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        g.nccl_connect(bytes(uid.cpu().numpy().tobytes()))
+        g.add_particles(sc.pos, sc.vel, sc.ids)
+        workload = (f"configs[4]: dense hex packing pitch 2.2r, pair+gravity+walls, {sc.n_global} particles in "
+                    f"{world} strips (weak scaling, {args.n} per GPU)")
+        parallelism = f"{world} strips over x, NCCL halo exchange + migration"
+    n = sc.n
     g.set_renderer_ready(False)
     g.synchronize()
     degree = len(sc.bonds) / n
@@ -221,19 +241,20 @@ def main():
     stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local))
 
     # ---- device-resident throughput ("value") -----------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     g.step_n(W)
     g.synchronize()
     l0 = g.launch_count
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    t_begin = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     g.step_n(args.steps)
     ev1.record(stream)
     g.synchronize()
     barrier()
-    clocks = sampler.stop()
+    t_end = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = g.launch_count - l0
     alive = g.num_particles
@@ -253,6 +274,7 @@ def main():
     g.step_n(args.steps)
     kt = g.kernel_times()
     g.enable_kernel_timing(False)
+    clocks = sampler.stop((t_begin, t_end))
     per_launch_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in kt.items()}
     dominant = max(("stage1", "stage2"), key=lambda k: per_launch_ms[k])
     peak, peak_src = hbm_peak()
@@ -296,6 +318,28 @@ def main():
            "ms_per_step": te / args.e2e_steps * 1e3,
            "note": "per step: ptoy_upload_state (pinned host -> device, re-binned) + ptoy_step_n(1) + ptoy_download_state"}
 
+    same_n1 = None
+    if world > 1 and rank == 0:
+        # like-for-like reference for the scaling figure: this rank's per-GPU workload as ONE strip
+        s1 = scenes.strip_scene(args.n, 0, 1)
+        g1 = ptoy_b200.Particles(device=local, default_scene=False)
+        g1.reset_scene(s1.domain)
+        g1.set_gravity(*s1.gravity)
+        g1.add_particles(s1.pos, s1.vel, s1.ids)
+        g1.set_renderer_ready(False)
+        g1.step_n(W)
+        g1.synchronize()
+        s1e = torch.cuda.ExternalStream(g1.stream, device=torch.device("cuda", local))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(s1e)
+        g1.step_n(args.steps)
+        a1.record(s1e)
+        g1.synchronize()
+        same_n1 = {"value": s1.n * args.steps / (a0.elapsed_time(a1) * 1e-3), "particles": s1.n,
+                   "note": "the per-GPU workload on one GPU without strips, timed in this run"}
+        g1.close()
+    if world > 1:
+        dist.barrier()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.ref_n)
@@ -306,10 +350,9 @@ def main():
             "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": ("configs[2]: 16M particles, hex pitch 2.02r, ~4 directed bonds/particle, 1% frozen"
-                                    if not args.no_bonds else "pair+gravity+walls only, hex pitch 2.02r"),
+            "config": {"workload": workload,
                        "particles_per_gpu": n, "mean_directed_bonds": degree, "frozen": int(len(sc.frozen)),
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent strips (weak)",
+                       "parallelism": parallelism, "single_gpu_same_workload": same_n1,
                        "l2": "inputs larger than L2 (working set %.1f GB per GPU)" % (n * 68 / 1e9),
                        "setup_s": t_setup},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

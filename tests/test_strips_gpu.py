@@ -89,10 +89,10 @@ def test_teleports_migrate_to_any_strip():
     by = top + 1.0                         # head room above the packing for the beam and the portals
     sc.domain = (ax, ay, bx, by)
     # a beam of fast particles flying into the left portal
-    yb = by - 0.6 + np.linspace(0, 0.3, 40)
-    beam = np.stack([np.full(40, ax + 0.3), yb], 1).astype(np.float32)
+    yb = by - 0.72 + 0.05 * np.arange(12)  # 0.05 apart: beyond the pair cutoff
+    beam = np.stack([np.full(12, ax + 0.3), yb], 1).astype(np.float32)
     sc.pos = np.concatenate([sc.pos, beam])
-    sc.vel = np.concatenate([sc.vel, np.tile(np.array([[8.0, 0.0]], np.float32), (40, 1))])
+    sc.vel = np.concatenate([sc.vel, np.tile(np.array([[8.0, 0.0]], np.float32), (12, 1))])
     sc.ids = np.arange(len(sc.pos), dtype=np.int32)
     sc.gravity = (False, (0.0, -10.0))
     x0, x1 = ax + 0.5, bx - 0.5
@@ -103,5 +103,5 @@ def test_teleports_migrate_to_any_strip():
     ref, _ = single(sc, 70, setup)
     got, _ = strips(sc, 70, 4, setup=setup)
     moved = ref["pos"][6000:, 0] > x1      # the beam came out of the far portal
-    assert moved.sum() >= 30
+    assert moved.sum() >= 8
     assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])

@@ -139,8 +139,8 @@ struct StageArgs {
   const int* bond_col;
   const int* slot_of_id;
   int has_bonds;
-  int* bslot;                  // [kBondPlan][cap] bond partner slots: written by stage 1, read by stage 2
-  unsigned char* bdeg;         // min(bond degree, 255), same hand-over
+  const int* bond_ell;         // bond table by id: 8 ints = first 6 partner ids (-1 pad), unused, degree
+  int* bslot;                  // [cap][8] partner slots + degree: written by stage 1, read by stage 2
   int cap;                     // stride of the slot-major bslot array
   // portals
   int n_sides;           // 2 * pairs

@@ -219,8 +219,7 @@ void Engine::ensure_capacity(size_t n) {
   pos_h_.alloc(nc);
   vel_h_.alloc(nc);
   newcell_.alloc(nc);
-  bslot_.alloc(nc * 6);
-  bdeg_.alloc(nc);
+  bslot_.alloc(nc * 8);
   for (int k = 0; k < 2; ++k) cell_[k].alloc(nc);  // rewritten by every reorder before use
   order_.alloc(nc);
   force_dbg_.release();
@@ -490,11 +489,20 @@ void Engine::sync_bonds() {
   for (auto& b : bonds_) ptr[(size_t)b.first + 1]++;
   for (size_t i = 0; i + 1 < ptr.size(); ++i) ptr[i + 1] += ptr[i];
   for (size_t e = 0; e < bonds_.size(); ++e) col[e] = bonds_[e].second;  // already row-major sorted
+  // the same rows as a fixed-width table (first 6 partners + degree): two 16-byte loads per id
+  std::vector<int> ell((id_cap_ + 1) * 8, -1);
+  for (size_t id = 0; id <= id_cap_; ++id) {
+    const uint32_t e0 = ptr[id], e1 = ptr[id + 1];
+    for (uint32_t k = 0; k < e1 - e0 && k < 6; ++k) ell[id * 8 + k] = col[e0 + k];
+    ell[id * 8 + 7] = (int)(e1 - e0);
+  }
+  bond_ell_.alloc(ell.size());
   bond_ptr_.alloc(ptr.size());
   bond_col_.alloc(col.size());
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   CUDA_CHECK(cudaMemcpy(bond_ptr_.p, ptr.data(), ptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(bond_col_.p, col.data(), col.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(bond_ell_.p, ell.data(), ell.size() * sizeof(int), cudaMemcpyHostToDevice));
 }
 
 void Engine::sync_frozen() {
@@ -693,7 +701,7 @@ StageArgs Engine::make_stage_args(int stage) {
   a.frozen_bits = frozen_bits_.p;
   a.has_bonds = !bonds_.empty();
   a.bond_ptr = bond_ptr_.p; a.bond_col = bond_col_.p; a.slot_of_id = slot_of_id_.p;
-  a.bslot = bslot_.p; a.bdeg = bdeg_.p;
+  a.bslot = bslot_.p; a.bond_ell = bond_ell_.p;
   a.cap = (int)cap_;
   a.n_sides = has_portal_tables_ ? (int)portals_.size() * 2 : 0;
   a.sides = sides_.p; a.pblk_ptr = pblk_ptr_.p; a.pblk = pblk_.p;

@@ -182,8 +182,8 @@ class Engine {
   DevBuf<float2> pos_[2], vel_[2], pos_h_, vel_h_, force_dbg_;
   DevBuf<int> id_[2], order_;
   DevBuf<uint32_t> cell_[2], newcell_;
-  DevBuf<int> bslot_;            // bond partner slots, slot-major: stage 1 -> stage 2
-  DevBuf<unsigned char> bdeg_;
+  DevBuf<int> bslot_;            // [cap][8] bond partner slots + degree: stage 1 -> stage 2
+  DevBuf<int> bond_ell_;         // [id_cap+1][8] bond table by id
   DevBuf<int> cnt_, start_;
   int n_items_ = 0;     // padded scan length
   DevBuf<unsigned long long> tile_state_;

@@ -16,8 +16,11 @@
 //   gather_kernel    deterministic (stable) reorder of pos/vel/id + id->slot map
 #include "common.h"
 
+#ifndef PTOY_SCAN_UNROLL
+#define PTOY_SCAN_UNROLL 2
+#endif
 #ifndef PTOY_STAGE_MINB
-#define PTOY_STAGE_MINB 4  // resident CTAs per SM the stage kernels are compiled for
+#define PTOY_STAGE_MINB 6  // resident CTAs per SM the stage kernels are compiled for
 #endif
 
 namespace ptoy {
@@ -225,7 +228,10 @@ __device__ __forceinline__ void eval_hit(const Phys& ph, float dx, float dy, flo
   }
 }
 
-template <int STAGE>
+// FEAT selects what the scene uses, so that unused force kinds cost neither instructions nor
+// registers: 1 = bonds, 2 = portals, 4 = mouse point force / pick (engine.cu picks the variant).
+constexpr int kFeatBonds = 1, kFeatPortals = 2, kFeatExtras = 4;
+template <int STAGE, int FEAT>
 __device__ __forceinline__ float2 particle_force(
     const StageArgs& a, const float2* __restrict__ X, HitQueue& hq, int slot, int pid, float2 x, float2 v,
     int Si, int Sj, float ui, float uj, int blk, unsigned flags) {
@@ -233,7 +239,7 @@ __device__ __forceinline__ float2 particle_force(
   float fx = 0.0f, fy = 0.0f;
   if (ph.gravity_enable) { fx = ph.gfx; fy = ph.gfy; }                       // :849-851
 
-  if (ph.force_enabled) {                                                    // :854-863
+  if ((FEAT & kFeatExtras) && ph.force_enabled) {                            // :854-863
     const float rx = fsub(x.x, ph.fcx), ry = fsub(x.y, ph.fcy);
     const float l = len2(rx, ry);
     if (l > ph.radius) {
@@ -251,7 +257,7 @@ __device__ __forceinline__ float2 particle_force(
     }
   }
 
-  if (flags & 2u) {                                                          // :866-871
+  if ((FEAT & kFeatPortals) && (flags & 2u)) {                               // :866-871
     for (int s = 0; s < a.n_sides; ++s) {
       const PortalSide ps = a.sides[s];
       float ex, ey;
@@ -262,7 +268,7 @@ __device__ __forceinline__ float2 particle_force(
     }
   }
 
-  if (ph.pick_enabled && pid == ph.pick_id) {                                // :874-876, :751-759
+  if ((FEAT & kFeatExtras) && ph.pick_enabled && pid == ph.pick_id) {        // :874-876, :751-759
     const float dx = fsub(x.x, ph.pkx), dy = fsub(x.y, ph.pky);
     const float r = len2(dx, dy);
     const float k = fdiv(fsub(ph.pickR, r), ph.pickR);
@@ -275,32 +281,29 @@ __device__ __forceinline__ float2 particle_force(
   fy = fsub(fy, fmul(v.y, ph.diss));
 
   // ---- bonds, part 1: partner slots and positions, fetched before the pair search starts so
-  // the loads overlap it.  Stage 1 resolves id -> CSR row -> partner id -> slot (three dependent
-  // gather levels, issued as batches of independent loads) and records the slots slot-major;
-  // stage 2 (same sorted order, same partners) just reads them back coalesced.
+  // the loads overlap it.  Stage 1 reads the particle's row of the bond table (8 ints per id: the
+  // first 6 partner ids in ascending = std::set order, the degree in the last; two 16-byte loads),
+  // resolves partner id -> slot with one batch of independent gathers and records the slots in
+  // one 32-byte sector per particle; stage 2 (same sorted order, same partners) reads them back
+  // with two 16-byte loads.
   int nb = 0;
   float2 bpos[kBondPlan];
   int bslot[kBondPlan];
-  if (a.has_bonds) {
+  if (FEAT & kFeatBonds) {
+    int4* hand = reinterpret_cast<int4*>(a.bslot) + 2 * (size_t)slot;
     if (STAGE == 1) {
-      const unsigned e0 = __ldg(a.bond_ptr + pid);
-      const unsigned ne = __ldg(a.bond_ptr + pid + 1) - e0;
-      nb = (int)(ne < 255u ? ne : 255u);
-      int bcol[kBondPlan];
-#pragma unroll
-      for (int k = 0; k < kBondPlan; ++k) bcol[k] = (k < nb) ? __ldg(a.bond_col + e0 + k) : -1;
+      const int4* row = reinterpret_cast<const int4*>(a.bond_ell) + 2 * (size_t)pid;
+      const int4 r0 = __ldg(row), r1 = __ldg(row + 1);
+      const int bcol[kBondPlan] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+      nb = r1.w;
 #pragma unroll
       for (int k = 0; k < kBondPlan; ++k) bslot[k] = (bcol[k] >= 0) ? a.slot_of_id[bcol[k]] : -1;
-      if (a.bslot) {
-#pragma unroll
-        for (int k = 0; k < kBondPlan; ++k)
-          if (k < nb) a.bslot[(size_t)k * a.cap + slot] = bslot[k];
-        a.bdeg[slot] = (unsigned char)nb;
-      }
+      hand[0] = make_int4(bslot[0], bslot[1], bslot[2], bslot[3]);
+      hand[1] = make_int4(bslot[4], bslot[5], -1, nb);
     } else {
-      nb = a.bdeg[slot];
-#pragma unroll
-      for (int k = 0; k < kBondPlan; ++k) bslot[k] = (k < nb) ? __ldg(a.bslot + (size_t)k * a.cap + slot) : -1;
+      const int4 r0 = hand[0], r1 = hand[1];
+      bslot[0] = r0.x; bslot[1] = r0.y; bslot[2] = r0.z; bslot[3] = r0.w; bslot[4] = r1.x; bslot[5] = r1.y;
+      nb = r1.w;
     }
 #pragma unroll
     for (int k = 0; k < kBondPlan; ++k) bpos[k] = (bslot[k] >= 0) ? __ldg(X + bslot[k]) : make_float2(0.f, 0.f);
@@ -332,12 +335,20 @@ __device__ __forceinline__ float2 particle_force(
       }
     };
     auto scan = [&](const float2* __restrict__ P, int q, int end) {
+#if PTOY_SCAN_UNROLL == 4
+      for (; q + 3 < end; q += 4) {
+        const float2 p0 = __ldg(P + q), p1 = __ldg(P + q + 1), p2 = __ldg(P + q + 2), p3 = __ldg(P + q + 3);
+        test(p0); test(p1); test(p2); test(p3);
+      }
+      for (; q < end; ++q) test(__ldg(P + q));
+#else
       for (; q + 1 < end; q += 2) {
         const float2 p0 = __ldg(P + q), p1 = __ldg(P + q + 1);
         test(p0);
         test(p1);
       }
       if (q < end) test(__ldg(P + q));
+#endif
     };
     for (int R = r_lo; R <= r_hi; ++R) {
       if (R >= a.g.own_lo && R < a.g.own_hi) {
@@ -377,7 +388,7 @@ __device__ __forceinline__ float2 particle_force(
   }
 
   // ---- bonds, part 2 (:761-826): CSR row of this id, partners ascending ----------------
-  if (a.has_bonds) {
+  if (FEAT & kFeatBonds) {
     auto one_bond = [&](int sb, float2 q) {
       if (sb < 0) return;  // partner left the grid: bond erased by CheckBonds (:205-215)
       float bx, by;
@@ -386,7 +397,7 @@ __device__ __forceinline__ float2 particle_force(
       const float ddx = fsub(x.x, q.x), ddy = fsub(x.y, q.y);
       const float dist = len2(ddx, ddy);
       bool found = false;
-      if (!(dist < ph.bond_cutoff)) {                                        // :784-819
+      if ((FEAT & kFeatPortals) && !(dist < ph.bond_cutoff)) {               // :784-819
         for (int s = 0; s < a.n_sides; ++s) {
           const PortalSide po = a.sides[s];
           const PortalSide ot = a.sides[s ^ 1];
@@ -415,8 +426,7 @@ __device__ __forceinline__ float2 particle_force(
       fy = fadd(fy, by);
     };
 #pragma unroll
-    for (int k = 0; k < kBondPlan; ++k)
-      if (k < nb) one_bond(bslot[k], bpos[k]);
+    for (int k = 0; k < kBondPlan; ++k) one_bond(bslot[k], bpos[k]);  // absent / dead partners are -1
     if (nb > kBondPlan) {  // more partners than the plan holds: walk the rest of the CSR row
       const unsigned e0 = __ldg(a.bond_ptr + pid), ne = __ldg(a.bond_ptr + pid + 1) - e0;
       for (unsigned e = kBondPlan; e < ne; ++e) {
@@ -427,7 +437,7 @@ __device__ __forceinline__ float2 particle_force(
   }
 
   // ---- cross-portal forces (:318-381) ------------------------------------------------
-  if (flags & 1u) {
+  if ((FEAT & kFeatPortals) && (flags & 1u)) {
     for (int s = 0; s < a.n_sides; ++s) {
       const int lb = a.pblk_ptr[s], le = a.pblk_ptr[s + 1];
       if (!in_sorted(a.pblk + lb, le - lb, blk)) continue;
@@ -571,7 +581,7 @@ __device__ __forceinline__ void key_and_count(const GridDev& g, const DistDev& d
   atomicAdd(cnt + key_of_packed(pc, g.SJ, g.ncell), 1);  // result unused -> RED.ADD
 }
 
-template <int STAGE>
+template <int STAGE, int FEAT>
 __global__ void __launch_bounds__(kThreads, PTOY_STAGE_MINB) stage_kernel(const __grid_constant__ StageArgs a) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.ctr->n_cur) return;
@@ -589,10 +599,10 @@ __global__ void __launch_bounds__(kThreads, PTOY_STAGE_MINB) stage_kernel(const 
   const float uj = fsub(x0.y, a.g.Ay) * a.g.inv_hsy - (float)(Sj - 4);
   int blk = 0;
   unsigned flags = 0u;
-  if (a.blk_flags) { blk = block_of_s(a.g, Si + a.g.row0, Sj); flags = a.blk_flags[blk]; }
+  if ((FEAT & kFeatPortals) && a.blk_flags) { blk = block_of_s(a.g, Si + a.g.row0, Sj); flags = a.blk_flags[blk]; }
   const int pid = a.need_id ? a.id[i] : 0;
 
-  float2 f = particle_force<STAGE>(a, X, hq, i, pid, x, v, Si, Sj, ui, uj, blk, flags);
+  float2 f = particle_force<STAGE, FEAT>(a, X, hq, i, pid, x, v, Si, Sj, ui, uj, blk, flags);
 
   bool frozen = false;
   if (a.has_frozen) frozen = (a.frozen_bits[pid >> 5] >> (pid & 31)) & 1u;
@@ -620,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, PTOY_STAGE_MINB) stage_kernel(const 
     float2 xn = make_float2(fadd(x0.x, fmul(vx, ph.dt)), fadd(x0.y, fmul(vy, ph.dt)));
     float2 vn = make_float2(vx, vy);
     if (a.do_tail) {
-      if (flags & 1u) teleport(a, blk, xn, vn);
+      if ((FEAT & kFeatPortals) && (flags & 1u)) teleport(a, blk, xn, vn);
       key_and_count(a.g, a.dist, xn, vn, pid, i, a.newcell, a.cnt);
     }
     a.pos_out[i] = xn;
@@ -900,10 +910,25 @@ __global__ void fill_i32_kernel(int* p, int v, size_t n) {
 // ---------------------------------------------------------------------------------
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
+template <int FEAT>
+static void launch_stage_feat(int stage, const StageArgs& a, int n_bound, cudaStream_t s) {
+  if (stage == 1) stage_kernel<1, FEAT><<<grid_for(n_bound), kThreads, 0, s>>>(a);
+  else stage_kernel<2, FEAT><<<grid_for(n_bound), kThreads, 0, s>>>(a);
+}
 void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound <= 0) return;
-  if (stage == 1) stage_kernel<1><<<grid_for(n_bound), kThreads, 0, s>>>(a);
-  else stage_kernel<2><<<grid_for(n_bound), kThreads, 0, s>>>(a);
+  const int feat = (a.has_bonds ? kFeatBonds : 0) | (a.n_sides > 0 ? kFeatPortals : 0) |
+                   ((a.ph.force_enabled || a.ph.pick_enabled) ? kFeatExtras : 0);
+  switch (feat) {
+    case 0: launch_stage_feat<0>(stage, a, n_bound, s); break;
+    case 1: launch_stage_feat<1>(stage, a, n_bound, s); break;
+    case 2: launch_stage_feat<2>(stage, a, n_bound, s); break;
+    case 3: launch_stage_feat<3>(stage, a, n_bound, s); break;
+    case 4: launch_stage_feat<4>(stage, a, n_bound, s); break;
+    case 5: launch_stage_feat<5>(stage, a, n_bound, s); break;
+    case 6: launch_stage_feat<6>(stage, a, n_bound, s); break;
+    default: launch_stage_feat<7>(stage, a, n_bound, s); break;
+  }
 }
 void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound - a.first <= 0) return;

@@ -135,6 +135,26 @@ def add_portals(scene, n_pairs, length=1.0, seed=7):
     return scene
 
 
+def reference_grid(domain):
+    """The block grid blocks::SetDomain (blocks.h:119-141) builds for `domain` starting from the
+    constructor's [-1,1]^2 grid: grow-only, whole blocks, by float32 accumulation.  Returns
+    (grid A.x, A.y, B.x, B.y, dims.i, dims.j) exactly as the engine / the reference compute them."""
+    f = np.float32
+    ax, ay, bx, by = f(-1), f(-1), f(1), f(1)
+    pa_x, pa_y, pb_x, pb_y = [f(v) for v in domain]
+    while pa_x < ax:
+        ax = f(ax - BLOCK)
+    while pa_y < ay:
+        ay = f(ay - BLOCK)
+    while pb_x > bx:
+        bx = f(bx + BLOCK)
+    while pb_y > by:
+        by = f(by + BLOCK)
+    di = int(f(f(bx - ax) / BLOCK)) + 1
+    dj = int(f(f(by - ay) / BLOCK)) + 1
+    return float(ax), float(ay), float(bx), float(by), di, dj
+
+
 def strip_scene(n_per_rank, rank, world, pitch_over_r=2.2, jitter_over_r=0.025, seed=1234, aspect=None):
     """Weak-scaling scene (configs[4]/[5] style dense packing): ONE global hex-packed scene of
     world * n_per_rank particles whose width grows with `world`; returns the particles of the
@@ -156,8 +176,7 @@ def strip_scene(n_per_rank, rank, world, pitch_over_r=2.2, jitter_over_r=0.025, 
     by = -1.0 + 2 * r + row_h * rows + pitch
     domain = (-1.0, -1.0, float(np.float32(bx)), float(np.float32(by)))
     bs = float(BLOCK)
-    di = int(np.float32(np.float32(domain[2]) - np.float32(-1.0)) / BLOCK) + 1
-    dj = int(np.float32(np.float32(domain[3]) - np.float32(-1.0)) / BLOCK) + 1
+    _, _, _, _, di, dj = reference_grid(domain)
     cb = partition_columns(di, world)
     # lattice columns that can fall into this rank's block columns (one extra on each side)
     x_lo, x_hi = -1.0 + cb[rank] * bs, -1.0 + cb[rank + 1] * bs

@@ -436,3 +436,104 @@ def test_full_size_properties_and_window_parity(n):
     core = (np.abs(sc.pos[sub] - c0) < half - 0.3).all(axis=1)
     sg = g.state_by_id(n)
     assert np.abs(sg["pos"][sub][core] - so["pos"][core]).max() < 1e-6
+
+
+# --------------------------------------------------------------------------- edge cases
+def test_empty_scene_and_single_particle():
+    """Empty input, one particle, adding nothing: the reference steps them without complaint."""
+    g, o = gpu(default_scene=False), best_oracle()
+    for p in (g, o):
+        p.reset_scene((-1, -1, 1, 1))
+    g.set_renderer_ready(False)
+    g.step_n(3)
+    o.step_n(3)
+    assert g.num_particles == o.num_particles == 0 and float(g.time) == float(o.time)
+    g.add_particles(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), np.zeros(0, np.int32))
+    assert g.num_particles == 0
+    one_p, one_v = np.array([[0.3, -0.2]], np.float32), np.array([[1.0, 2.0]], np.float32)
+    for p in (g, o):
+        p.add_particles(one_p, one_v, np.array([7], np.int32))   # ids need not start at 0
+    g.step_n(50)
+    o.step_n(50)
+    sg, so = g.state_by_id(8), o.state_by_id(8)
+    # (ids 0..6 were never added: the reference's id map value-initialises them to block 0, slot 0)
+    assert bits_equal(sg["pos"][7], so["pos"][7]) and bits_equal(sg["vel"][7], so["vel"][7])   # no pair sums: bit-exact
+    assert sg["block"][7] == so["block"][7] and np.all(sg["block"][:7] == -1)
+
+
+def test_particles_outside_the_grid_are_skipped_on_insert():
+    """blocks::AddParticles (blocks.h:186-191) ignores positions that FindBlock rejects, keeps the
+    band below the low edges (truncation toward zero) and NaNs never enter."""
+    pos = np.array([[0.0, 0.0], [5.0, 0.0], [-1.05, -1.0], [-1.09, 0.0], [np.nan, 0.0], [0.5, 1.079], [0.5, 1.081]],
+                   np.float32)
+    g, o = gpu(default_scene=False), best_oracle()
+    for p in (g, o):
+        p.reset_scene((-1, -1, 1, 1))
+        p.set_gravity(False)
+        p.add_particles(pos, np.zeros_like(pos), np.arange(len(pos), dtype=np.int32))
+    sg, so = g.state_by_id(len(pos)), o.state_by_id(len(pos))
+    inside = np.array([0, 2, 5])
+    assert np.array_equal(np.nonzero(sg["block"] >= 0)[0], inside)
+    assert np.array_equal(sg["block"][inside], so["block"][inside])
+    # (the reference's id map value-initialises the skipped ids to block 0, slot 0; the count is right)
+    assert g.num_particles == o.num_particles == 3
+
+
+def test_dense_cell_and_coincident_particles():
+    """Many particles in one sub-cell (hit queue flushes, multi-entry stable reorder) and exactly
+    coincident particles (dp = 0: zero force in the reference)."""
+    rng = np.random.RandomState(2)
+    cluster = (np.array([0.101, 0.203]) + rng.uniform(0, 0.03, size=(40, 2))).astype(np.float32)
+    twins = np.array([[0.5, 0.5], [0.5, 0.5], [-0.5, 0.5], [-0.5, 0.5]], np.float32)
+    pos = np.concatenate([cluster, twins])
+    g, o = gpu(default_scene=False), best_oracle()
+    for p in (g, o):
+        p.reset_scene((-1, -1, 1, 1))
+        p.add_particles(pos, np.zeros_like(pos), np.arange(len(pos), dtype=np.int32))
+    g.set_renderer_ready(False)
+    n = len(pos)
+    f = g.eval_forces(1, n)
+    o2 = best_oracle()
+    o2.reset_scene((-1, -1, 1, 1))
+    o2.add_particles(pos, np.zeros_like(pos), np.arange(n, dtype=np.int32))
+    o2.eval_forces()
+    fo = o2.state_by_id(n)["force"]
+    scale = force_scale(pos, fo)
+    assert (np.abs(f - fo).max(axis=1) / scale).max() <= FORCE_RTOL
+    assert bits_equal(f[40:], fo[40:])          # coincident pairs feel gravity only, bit for bit
+    g.step_n(1)
+    o.step_n(1)
+    sg, so = g.state_by_id(n), o.state_by_id(n)
+    assert np.array_equal(sg["block"], so["block"])
+    assert np.abs(sg["vel"] - so["vel"]).max() <= 1e-4 * np.abs(so["vel"]).max()
+
+
+def test_many_bonds_on_one_particle():
+    """A hub with 12 bonds: more than the six the kernels resolve up front (CSR tail path)."""
+    hub = np.array([[0.0, 0.0]], np.float32)
+    th = np.linspace(0, 2 * np.pi, 12, endpoint=False)
+    ring = np.stack([0.05 * np.cos(th), 0.05 * np.sin(th)], 1).astype(np.float32)
+    pos = np.concatenate([hub, ring])
+    bonds = np.array([[0, k] for k in range(1, 13)] + [[k, 0] for k in range(1, 13)], np.int32)
+    g, o = gpu(default_scene=False), best_oracle()
+    for p in (g, o):
+        p.reset_scene((-1, -1, 1, 1))
+        p.set_gravity(False)
+        p.add_particles(pos, np.zeros_like(pos), np.arange(13, dtype=np.int32))
+        p.set_bonds(bonds)
+    g.set_renderer_ready(False)
+    twin = best_oracle()
+    twin.reset_scene((-1, -1, 1, 1))
+    twin.set_gravity(False)
+    twin.add_particles(pos, np.zeros_like(pos), np.arange(13, dtype=np.int32))
+    twin.set_bonds(bonds)
+    twin.eval_forces()
+    fo = twin.state_by_id(13)["force"]
+    f = g.eval_forces(1, 13)
+    assert (np.abs(f - fo).max(axis=1) / force_scale(pos, fo, bonds, 0.0)).max() <= FORCE_RTOL
+    # a stiff, symmetric, overlapping configuration: compare a short horizon
+    g.step_n(3)
+    o.step_n(3)
+    sg, so = g.state_by_id(13), o.state_by_id(13)
+    assert np.abs(sg["pos"] - so["pos"]).max() < 1e-6
+    assert np.array_equal(g.get_bonds(), o.get_bonds())

@@ -142,6 +142,8 @@ struct StageArgs {
   const int* bond_ell;         // bond table by id: 8 ints = first 6 partner ids (-1 pad), unused, degree
   int* bslot;                  // [cap][8] partner slots + degree: written by stage 1, read by stage 2
   int cap;                     // stride of the slot-major bslot array
+  int ghost_cap;               // decoding of ghost references in slot_of_id (GhostMapArgs)
+  int* err;                    // sticky error bits (Counters::err_flags)
   // portals
   int n_sides;           // 2 * pairs
   const PortalSide* sides;
@@ -222,7 +224,20 @@ struct GhostPackArgs {   // boundary rows -> contiguous staging buffers for the 
   int ghost_cap;
   float2* out_pos[2];
   int* out_start[2];  // 2*SJ+1 entries, rebased to 0; nullptr = positions only (same layout as before)
+  const int* id;      // with out_id: particle ids of the same rows (bonds across strips)
+  int* out_id[2];
   int* err;
+};
+
+// Bonds across strips: the ids of the neighbours' boundary rows are entered into the id -> slot
+// map as ghost references  -2 - (side * ghost_cap + index)  so that a bond partner that lives in
+// a ghost row is found like a local one (kernels.cu bond_partner_pos).
+struct GhostMapArgs {
+  int* slot_of_id;
+  const int* ids[2];      // ghost ids per side
+  const int* gstart[2];   // ghost start slices: count = gstart[2*SJ] - gstart[0]
+  int* count[2];          // mark: written (remembered for the next unmark); unmark: read
+  int SJ, ghost_cap, mark;
 };
 
 // launchers (kernels.cu)
@@ -235,6 +250,7 @@ void launch_gather(const ReorderArgs& a, int n_bound, cudaStream_t s);
 void launch_finalize(Counters* ctr, int* ticket, cudaStream_t s);
 void launch_arrivals(const ArrivalArgs& a, cudaStream_t s);
 void launch_ghost_pack(const GhostPackArgs& a, cudaStream_t s);
+void launch_ghost_map(const GhostMapArgs& a, cudaStream_t s);
 void launch_find_blocks(const GridDev& g, const float2* pos, size_t n, long long* out, cudaStream_t s);
 void launch_state_by_id(const GridDev& g, const Counters* ctr, const float2* pos, const float2* vel,
                         const int* id, int n_bound, float2* pos_by_id, float2* vel_by_id,

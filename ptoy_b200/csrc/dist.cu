@@ -110,7 +110,12 @@ void Engine::alloc_strip_buffers() {
     s.ghost_start[sd].alloc(nstart);
     CUDA_CHECK(cudaMemsetAsync(s.ghost_start[sd].p, 0, nstart * sizeof(int), stream_));
     CUDA_CHECK(cudaMemsetAsync(s.send_start[sd].p, 0, nstart * sizeof(int), stream_));
+    s.send_id[sd].alloc(s.ghost_cap);
+    s.ghost_id[sd][0].alloc(s.ghost_cap);
+    s.ghost_id[sd][1].alloc(s.ghost_cap);
   }
+  s.ghost_n.alloc(2);
+  CUDA_CHECK(cudaMemsetAsync(s.ghost_n.p, 0, 2 * sizeof(int), stream_));
   const size_t bytes = (size_t)mig_stride(s.out_cap) * s.world;
   s.outbox.alloc(bytes);
   s.inbox.alloc(bytes);
@@ -152,12 +157,39 @@ void Engine::phase_pack_halo(int stage) {
   for (int sd = 0; sd < 2; ++sd) {
     g.out_pos[sd] = strip_.send_pos[sd].p;
     g.out_start[sd] = stage == 1 ? strip_.send_start[sd].p : nullptr;
+    g.out_id[sd] = (stage == 1 && !bonds_.empty()) ? strip_.send_id[sd].p : nullptr;
   }
+  g.id = id_[cur_].p;
   g.err = &ctr_.p->err_flags;
   if (cap_ == 0) return;
   begin_timed(5);
   launch_ghost_pack(g, stream_);
   end_timed();
+}
+
+// After the stage-1 halo: enter the neighbours' boundary-row ids into the id -> slot map as ghost
+// references (and forget the previous iteration's), so bonds reach across the strip boundary.
+void Engine::phase_ghost_map() {
+  if (strip_.world == 1 || bonds_.empty()) return;
+  StripState& s = strip_;
+  GhostMapArgs g{};
+  g.slot_of_id = slot_of_id_.p;
+  g.SJ = grid_.SJ;
+  g.ghost_cap = s.ghost_cap;
+  for (int pass = 0; pass < 2; ++pass) {
+    g.mark = pass;
+    for (int sd = 0; sd < 2; ++sd) {
+      const bool have = sd == 0 ? s.rank > 0 : s.rank + 1 < s.world;
+      // unmark reads last iteration's ids, mark the ones just received
+      g.ids[sd] = have ? s.ghost_id[sd][pass ? s.ghost_cur : s.ghost_cur ^ 1].p : nullptr;
+      g.gstart[sd] = s.ghost_start[sd].p;
+      g.count[sd] = s.ghost_n.p + sd;
+    }
+    begin_timed(5);
+    launch_ghost_map(g, stream_);
+    end_timed();
+  }
+  s.ghost_cur ^= 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -194,11 +226,13 @@ struct LocalGroup : Transport {
         StripState& l = e[r - 1]->strip_mut();
         copy(stage == 1 ? l.ghost_pos[1].p : l.ghost_pos_h[1].p, me.send_pos[0].p, pb);
         if (stage == 1) copy(l.ghost_start[1].p, me.send_start[0].p, sb);
+        if (stage == 1 && e[r]->has_bonds()) copy(l.ghost_id[1][l.ghost_cur].p, me.send_id[0].p, pb / 2);
       }
       if (r + 1 < n) {  // my last rows -> right neighbour's left ghost
         StripState& rr = e[r + 1]->strip_mut();
         copy(stage == 1 ? rr.ghost_pos[0].p : rr.ghost_pos_h[0].p, me.send_pos[1].p, pb);
         if (stage == 1) copy(rr.ghost_start[0].p, me.send_start[1].p, sb);
+        if (stage == 1 && e[r]->has_bonds()) copy(rr.ghost_id[0][rr.ghost_cur].p, me.send_id[1].p, pb / 2);
       }
     }
   }
@@ -219,6 +253,7 @@ struct LocalGroup : Transport {
       for (auto* x : e) x->phase_prepare();
       for (auto* x : e) x->phase_pack_halo(1);
       halo_all(1);
+      for (auto* x : e) x->phase_ghost_map();
       for (auto* x : e) x->phase_stage1();
       for (auto* x : e) x->phase_pack_halo(2);
       halo_all(2);
@@ -255,6 +290,10 @@ struct NcclTransport : Transport {
       if (stage == 1) {
         NCCL_CHECK(NcclApi::get().Send(s.send_start[sd].p, sb, ncclChar, peer, comm, e.stream()));
         NCCL_CHECK(NcclApi::get().Recv(s.ghost_start[sd].p, sb, ncclChar, peer, comm, e.stream()));
+        if (e.has_bonds()) {  // every rank holds the same bond set, so both ends agree
+          NCCL_CHECK(NcclApi::get().Send(s.send_id[sd].p, pb / 2, ncclChar, peer, comm, e.stream()));
+          NCCL_CHECK(NcclApi::get().Recv(s.ghost_id[sd][s.ghost_cur].p, pb / 2, ncclChar, peer, comm, e.stream()));
+        }
       }
     }
     NCCL_CHECK(NcclApi::get().GroupEnd());

@@ -703,6 +703,8 @@ StageArgs Engine::make_stage_args(int stage) {
   a.bond_ptr = bond_ptr_.p; a.bond_col = bond_col_.p; a.slot_of_id = slot_of_id_.p;
   a.bslot = bslot_.p; a.bond_ell = bond_ell_.p;
   a.cap = (int)cap_;
+  a.ghost_cap = strip_.ghost_cap;
+  a.err = &ctr_.p->err_flags;
   a.n_sides = has_portal_tables_ ? (int)portals_.size() * 2 : 0;
   a.sides = sides_.p; a.pblk_ptr = pblk_ptr_.p; a.pblk = pblk_.p;
   a.blk_flags = has_portal_tables_ ? blk_flags_.p : nullptr;
@@ -814,10 +816,7 @@ void Engine::phase_prepare() {
   sync_env();
   sync_bonds();
   sync_frozen();
-  if (!bonds_.empty()) {
-    if (strip_.world > 1) throw Error(-3, "bonds are not supported across strips yet (DESIGN.md §7)");
-    ensure_slot_map();
-  }
+  if (!bonds_.empty()) ensure_slot_map();
   t_half_ = (float)((double)t_ + 0.5 * (double)dt_);                      // :126
   // The serial tail's resize decision (:157-175) depends on host state only, so it is
   // taken up front: if the block grid grows, portals are detected after the re-binning.
@@ -898,7 +897,7 @@ void Engine::phase_end() {
 
 void Engine::iterate() {
   phase_prepare();
-  if (transport_) { phase_pack_halo(1); transport_->halo(*this, 1); }
+  if (transport_) { phase_pack_halo(1); transport_->halo(*this, 1); phase_ghost_map(); }
   phase_stage1();
   if (transport_) { phase_pack_halo(2); transport_->halo(*this, 2); }
   phase_stage2();

@@ -49,6 +49,9 @@ struct StripState {
   DevBuf<int> send_start[2];
   DevBuf<float2> ghost_pos[2], ghost_pos_h[2];  // neighbours' boundary rows: at x0 / at x_half
   DevBuf<int> ghost_start[2];
+  DevBuf<int> send_id[2], ghost_id[2][2];  // ids of the boundary rows (bonds across strips); [side][cur/prev]
+  DevBuf<int> ghost_n;                     // [2] ghosts entered into the id -> slot map last iteration
+  int ghost_cur = 0;
   DevBuf<unsigned char> outbox, inbox; // world blocks each (common.h DistDev layout)
   DevBuf<unsigned long long> arr_vkey;
 };
@@ -117,7 +120,9 @@ class Engine {
   StripState& strip_mut() { return strip_; }
   void phase_prepare();        // host bookkeeping: dirty state -> device, resize decision
   void phase_pack_halo(int stage);   // boundary rows -> send buffers (stage 1: x0 + start slice, 2: x_half)
+  void phase_ghost_map();      // neighbours' boundary ids -> id -> slot map (bonds across strips)
   void phase_stage1();
+  bool has_bonds() const { return !bonds_.empty(); }
   void phase_stage2();
   void phase_reorder();        // arrivals + reorder
   void phase_end();            // snapshot, time

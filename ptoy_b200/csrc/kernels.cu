@@ -210,6 +210,19 @@ __device__ __forceinline__ bool in_sorted(const int* __restrict__ list, int n, i
 // all forces on one particle (particles.cpp:839-910 calc_forces, :761-826 RHS_bonds,
 // :318-381 ApplyPortalsForces), summed in the reference's order of force kinds
 // ---------------------------------------------------------------------------------
+// Position of a bond partner given its entry in the id -> slot map: a local slot (>= 0), a ghost
+// reference -2 - (side * ghost_cap + index) into the neighbour strip's boundary rows, or -1
+// (partner left the grid: the bond is erased by CheckBonds, particles.cpp:205-215).
+__device__ __forceinline__ float2 bond_partner_pos(const StageArgs& a, const float2* __restrict__ X, int sb) {
+  if (sb >= 0) return __ldg(X + sb);
+  if (sb <= -2) {
+    const int code = -2 - sb;
+    const int side = code >= a.ghost_cap;
+    return __ldg(a.gpos[side] + (code - side * a.ghost_cap));
+  }
+  return make_float2(0.f, 0.f);
+}
+
 constexpr int kHitQueue = 6;     // pending in-range pairs per thread (shared memory)
 constexpr int kBondPlan = 6;     // bond partners per particle resolved up front / handed from stage 1 to stage 2
 struct HitQueue {
@@ -298,6 +311,12 @@ __device__ __forceinline__ float2 particle_force(
       nb = r1.w;
 #pragma unroll
       for (int k = 0; k < kBondPlan; ++k) bslot[k] = (bcol[k] >= 0) ? a.slot_of_id[bcol[k]] : -1;
+      if (a.dist.world > 1) {  // strips: a partner that is neither local nor in a ghost row cannot be served
+        bool lost = false;
+#pragma unroll
+        for (int k = 0; k < kBondPlan; ++k) lost |= bcol[k] >= 0 && bslot[k] == -1;
+        if (lost) atomicOr(a.err, 16);
+      }
       hand[0] = make_int4(bslot[0], bslot[1], bslot[2], bslot[3]);
       hand[1] = make_int4(bslot[4], bslot[5], -1, nb);
     } else {
@@ -306,7 +325,7 @@ __device__ __forceinline__ float2 particle_force(
       nb = r1.w;
     }
 #pragma unroll
-    for (int k = 0; k < kBondPlan; ++k) bpos[k] = (bslot[k] >= 0) ? __ldg(X + bslot[k]) : make_float2(0.f, 0.f);
+    for (int k = 0; k < kBondPlan; ++k) bpos[k] = bond_partner_pos(a, X, bslot[k]);
   }
 
   // ---- pair forces (:884-900 + :598-606) over the sub-cell neighbourhood ----------------
@@ -390,7 +409,7 @@ __device__ __forceinline__ float2 particle_force(
   // ---- bonds, part 2 (:761-826): CSR row of this id, partners ascending ----------------
   if (FEAT & kFeatBonds) {
     auto one_bond = [&](int sb, float2 q) {
-      if (sb < 0) return;  // partner left the grid: bond erased by CheckBonds (:205-215)
+      if (sb == -1) return;  // partner left the grid: bond erased by CheckBonds (:205-215)
       float bx, by;
       // p_pos.dist(q_pos) = |q - p| and F12_bond's |p - q| are the same float: the differences
       // are exact negatives of each other, so one sqrt serves both (particles.cpp:731,779)
@@ -431,7 +450,7 @@ __device__ __forceinline__ float2 particle_force(
       const unsigned e0 = __ldg(a.bond_ptr + pid), ne = __ldg(a.bond_ptr + pid + 1) - e0;
       for (unsigned e = kBondPlan; e < ne; ++e) {
         const int sb = a.slot_of_id[a.bond_col[e0 + e]];
-        one_bond(sb, sb >= 0 ? __ldg(X + sb) : make_float2(0.f, 0.f));
+        one_bond(sb, bond_partner_pos(a, X, sb));
       }
     }
   }
@@ -845,7 +864,10 @@ __global__ void __launch_bounds__(kThreads) ghost_pack_kernel(const __grid_const
   const int c0 = a.row_lo[side] * a.SJ;
   const int b0 = a.start[c0], b1 = a.start[c0 + 2 * a.SJ];
   if (t == 0 && b1 - b0 > a.ghost_cap) atomicOr(a.err, 4);
-  if (t < b1 - b0 && t < a.ghost_cap) a.out_pos[side][t] = a.X[b0 + t];
+  if (t < b1 - b0 && t < a.ghost_cap) {
+    a.out_pos[side][t] = a.X[b0 + t];
+    if (a.out_id[side]) a.out_id[side][t] = a.id[b0 + t];
+  }
   if (a.out_start[side] && t <= 2 * a.SJ) a.out_start[side][t] = a.start[c0 + t] - b0;
 }
 
@@ -946,6 +968,26 @@ void launch_fill(const ReorderArgs& a, int n_bound, cudaStream_t s) {
 void launch_gather(const ReorderArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound <= 0) return;
   gather_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(a);
+}
+__global__ void __launch_bounds__(kThreads) ghost_map_kernel(const __grid_constant__ GhostMapArgs a) {
+  const int side = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  if (a.ids[side] == nullptr) return;
+  if (a.mark) {
+    const int n = min(a.gstart[side][2 * a.SJ] - a.gstart[side][0], a.ghost_cap);
+    if (t == 0) *a.count[side] = n;
+    if (t < n) a.slot_of_id[a.ids[side][t]] = -2 - (side * a.ghost_cap + t);
+  } else {
+    // forget last iteration's ghosts (an id that became local meanwhile holds a slot >= 0: keep it)
+    if (t < *a.count[side]) {
+      const int pid = a.ids[side][t];
+      if (a.slot_of_id[pid] <= -2) a.slot_of_id[pid] = -1;
+    }
+  }
+}
+
+void launch_ghost_map(const GhostMapArgs& a, cudaStream_t s) {
+  ghost_map_kernel<<<dim3(grid_for((size_t)a.ghost_cap), 2), kThreads, 0, s>>>(a);
 }
 void launch_arrivals(const ArrivalArgs& a, cudaStream_t s) {
   arrivals_kernel<<<grid_for((size_t)a.world * a.in_cap), kThreads, 0, s>>>(a);

@@ -105,3 +105,20 @@ def test_teleports_migrate_to_any_strip():
     moved = ref["pos"][6000:, 0] > x1      # the beam came out of the far portal
     assert moved.sum() >= 8
     assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_strips_with_bonds_across_the_boundaries(world):
+    """configs[2]-style scene (bond network, frozen particles) cut into strips: bond partners in
+    the neighbour strip are found through the ghost ids; bonded particles migrate with their
+    bonds (every strip holds the bond table by id)."""
+    sc = scenes.hex_lattice(24000, 2.02, 0.01, seed=31, vel_scale=1.5)
+    scenes.add_lattice_bonds(sc)
+
+    def setup(p):
+        p.set_bonds(sc.bonds)
+        p.set_frozen(sc.frozen)
+    ref, n_ref = single(sc, 40, setup)
+    got, n_got = strips(sc, 40, world, setup=setup)
+    assert n_got == n_ref == sc.n
+    assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])

@@ -213,9 +213,10 @@ __device__ __forceinline__ bool in_sorted(const int* __restrict__ list, int n, i
 // Position of a bond partner given its entry in the id -> slot map: a local slot (>= 0), a ghost
 // reference -2 - (side * ghost_cap + index) into the neighbour strip's boundary rows, or -1
 // (partner left the grid: the bond is erased by CheckBonds, particles.cpp:205-215).
+template <bool STRIPS>
 __device__ __forceinline__ float2 bond_partner_pos(const StageArgs& a, const float2* __restrict__ X, int sb) {
   if (sb >= 0) return __ldg(X + sb);
-  if (sb <= -2) {
+  if (STRIPS && sb <= -2) {
     const int code = -2 - sb;
     const int side = code >= a.ghost_cap;
     return __ldg(a.gpos[side] + (code - side * a.ghost_cap));
@@ -242,8 +243,9 @@ __device__ __forceinline__ void eval_hit(const Phys& ph, float dx, float dy, flo
 }
 
 // FEAT selects what the scene uses, so that unused force kinds cost neither instructions nor
-// registers: 1 = bonds, 2 = portals, 4 = mouse point force / pick (engine.cu picks the variant).
-constexpr int kFeatBonds = 1, kFeatPortals = 2, kFeatExtras = 4;
+// registers: 1 = bonds, 2 = portals, 4 = mouse point force / pick, 8 = strip decomposition
+// (ghost rows, ghost bond partners); launch_stage picks the variant.
+constexpr int kFeatBonds = 1, kFeatPortals = 2, kFeatExtras = 4, kFeatStrips = 8;
 template <int STAGE, int FEAT>
 __device__ __forceinline__ float2 particle_force(
     const StageArgs& a, const float2* __restrict__ X, HitQueue& hq, int slot, int pid, float2 x, float2 v,
@@ -311,7 +313,7 @@ __device__ __forceinline__ float2 particle_force(
       nb = r1.w;
 #pragma unroll
       for (int k = 0; k < kBondPlan; ++k) bslot[k] = (bcol[k] >= 0) ? a.slot_of_id[bcol[k]] : -1;
-      if (a.dist.world > 1) {  // strips: a partner that is neither local nor in a ghost row cannot be served
+      if (FEAT & kFeatStrips) {  // a partner that is neither local nor in a ghost row cannot be served
         bool lost = false;
 #pragma unroll
         for (int k = 0; k < kBondPlan; ++k) lost |= bcol[k] >= 0 && bslot[k] == -1;
@@ -325,7 +327,7 @@ __device__ __forceinline__ float2 particle_force(
       nb = r1.w;
     }
 #pragma unroll
-    for (int k = 0; k < kBondPlan; ++k) bpos[k] = bond_partner_pos(a, X, bslot[k]);
+    for (int k = 0; k < kBondPlan; ++k) bpos[k] = bond_partner_pos<(FEAT & kFeatStrips) != 0>(a, X, bslot[k]);
   }
 
   // ---- pair forces (:884-900 + :598-606) over the sub-cell neighbourhood ----------------
@@ -370,7 +372,7 @@ __device__ __forceinline__ float2 particle_force(
 #endif
     };
     for (int R = r_lo; R <= r_hi; ++R) {
-      if (R >= a.g.own_lo && R < a.g.own_hi) {
+      if (!(FEAT & kFeatStrips) || (R >= a.g.own_lo && R < a.g.own_hi)) {
         const int base = R * a.g.SJ;
         const int beg = __ldg(a.start + base + c_lo), end = __ldg(a.start + base + c_hi + 1);
         if (R == Si) {
@@ -450,7 +452,7 @@ __device__ __forceinline__ float2 particle_force(
       const unsigned e0 = __ldg(a.bond_ptr + pid), ne = __ldg(a.bond_ptr + pid + 1) - e0;
       for (unsigned e = kBondPlan; e < ne; ++e) {
         const int sb = a.slot_of_id[a.bond_col[e0 + e]];
-        one_bond(sb, bond_partner_pos(a, X, sb));
+        one_bond(sb, bond_partner_pos<(FEAT & kFeatStrips) != 0>(a, X, sb));
       }
     }
   }
@@ -940,7 +942,8 @@ static void launch_stage_feat(int stage, const StageArgs& a, int n_bound, cudaSt
 void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound <= 0) return;
   const int feat = (a.has_bonds ? kFeatBonds : 0) | (a.n_sides > 0 ? kFeatPortals : 0) |
-                   ((a.ph.force_enabled || a.ph.pick_enabled) ? kFeatExtras : 0);
+                   ((a.ph.force_enabled || a.ph.pick_enabled) ? kFeatExtras : 0) |
+                   (a.dist.world > 1 ? kFeatStrips : 0);
   switch (feat) {
     case 0: launch_stage_feat<0>(stage, a, n_bound, s); break;
     case 1: launch_stage_feat<1>(stage, a, n_bound, s); break;
@@ -949,7 +952,15 @@ void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s) {
     case 4: launch_stage_feat<4>(stage, a, n_bound, s); break;
     case 5: launch_stage_feat<5>(stage, a, n_bound, s); break;
     case 6: launch_stage_feat<6>(stage, a, n_bound, s); break;
-    default: launch_stage_feat<7>(stage, a, n_bound, s); break;
+    case 7: launch_stage_feat<7>(stage, a, n_bound, s); break;
+    case 8: launch_stage_feat<8>(stage, a, n_bound, s); break;
+    case 9: launch_stage_feat<9>(stage, a, n_bound, s); break;
+    case 10: launch_stage_feat<10>(stage, a, n_bound, s); break;
+    case 11: launch_stage_feat<11>(stage, a, n_bound, s); break;
+    case 12: launch_stage_feat<12>(stage, a, n_bound, s); break;
+    case 13: launch_stage_feat<13>(stage, a, n_bound, s); break;
+    case 14: launch_stage_feat<14>(stage, a, n_bound, s); break;
+    default: launch_stage_feat<15>(stage, a, n_bound, s); break;
   }
 }
 void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s) {

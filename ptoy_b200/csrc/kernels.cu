@@ -16,11 +16,19 @@
 //   gather_kernel    deterministic (stable) reorder of pos/vel/id + id->slot map
 #include "common.h"
 
+#ifndef PTOY_ROW_PREFETCH
+#define PTOY_ROW_PREFETCH 1
+#endif
 #ifndef PTOY_SCAN_UNROLL
 #define PTOY_SCAN_UNROLL 2
 #endif
+// resident CTAs per SM the stage kernels are compiled for (measured on B200: 40 registers win
+// without bonds, 48 with the bond partner prefetch)
 #ifndef PTOY_STAGE_MINB
-#define PTOY_STAGE_MINB 6  // resident CTAs per SM the stage kernels are compiled for
+#define PTOY_STAGE_MINB 6
+#endif
+#ifndef PTOY_STAGE_MINB_BONDS
+#define PTOY_STAGE_MINB_BONDS 5
 #endif
 
 namespace ptoy {
@@ -371,6 +379,28 @@ __device__ __forceinline__ float2 particle_force(
       if (q < end) test(__ldg(P + q));
 #endif
     };
+#if PTOY_ROW_PREFETCH
+    if (!(FEAT & kFeatStrips)) {
+      // the three rows every particle needs: all six cell offsets are loaded before the first
+      // scan; the rare extra rows (fractional position within the margin of a cell edge) follow
+      const int* sp = a.start + (Si - 1) * a.g.SJ;
+      const int b0 = __ldg(sp + c_lo), e0 = __ldg(sp + c_hi + 1);
+      const int b1 = __ldg(sp + a.g.SJ + c_lo), e1 = __ldg(sp + a.g.SJ + c_hi + 1);
+      const int b2 = __ldg(sp + 2 * a.g.SJ + c_lo), e2 = __ldg(sp + 2 * a.g.SJ + c_hi + 1);
+      scan(X, b0, e0);
+      scan(X, b1, slot);
+      scan(X, slot + 1, e1);
+      scan(X, b2, e2);
+      if (r_lo < Si - 1) {
+        const int* s2 = a.start + (Si - 2) * a.g.SJ;
+        scan(X, __ldg(s2 + c_lo), __ldg(s2 + c_hi + 1));
+      }
+      if (r_hi > Si + 1) {
+        const int* s2 = a.start + (Si + 2) * a.g.SJ;
+        scan(X, __ldg(s2 + c_lo), __ldg(s2 + c_hi + 1));
+      }
+    } else
+#endif
     for (int R = r_lo; R <= r_hi; ++R) {
       if (!(FEAT & kFeatStrips) || (R >= a.g.own_lo && R < a.g.own_hi)) {
         const int base = R * a.g.SJ;
@@ -603,7 +633,7 @@ __device__ __forceinline__ void key_and_count(const GridDev& g, const DistDev& d
 }
 
 template <int STAGE, int FEAT>
-__global__ void __launch_bounds__(kThreads, PTOY_STAGE_MINB) stage_kernel(const __grid_constant__ StageArgs a) {
+__global__ void __launch_bounds__(kThreads, (FEAT & kFeatBonds) ? PTOY_STAGE_MINB_BONDS : PTOY_STAGE_MINB) stage_kernel(const __grid_constant__ StageArgs a) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.ctr->n_cur) return;
   const float2 x0 = a.pos[i];

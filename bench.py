@@ -187,6 +187,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    import faulthandler
     import torch
     import torch.distributed as dist
     import ptoy_b200
@@ -195,6 +196,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # a stalled collective must not hold the box: dump the Python stacks and exit after a while
+    faulthandler.dump_traceback_later(int(os.environ.get("PTOY_WATCHDOG_S", "420")), exit=True)
+
+    def progress(msg):
+        if os.environ.get("PTOY_BENCH_VERBOSE"):
+            print(f"[rank {rank} {time.time() % 1000:7.2f}] {msg}", file=sys.stderr, flush=True)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -226,8 +233,11 @@ def main():
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(ptoy_b200.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
+        progress("scene built, connecting NCCL")
         g.nccl_connect(bytes(uid.cpu().numpy().tobytes()))
+        progress("connected")
         g.add_particles(sc.pos, sc.vel, sc.ids)
+        progress("particles added")
         workload = (f"configs[4]: dense hex packing pitch 2.2r, pair+gravity+walls, {sc.n_global} particles in "
                     f"{world} strips (weak scaling, {args.n} per GPU)")
         parallelism = f"{world} strips over x, NCCL halo exchange + migration"
@@ -243,8 +253,12 @@ def main():
     # ---- device-resident throughput ("value") -----------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    g.step_n(W)
+    g.step_n(1)
     g.synchronize()
+    progress("first step done")
+    g.step_n(W - 1)
+    g.synchronize()
+    progress("warm-up done")
     l0 = g.launch_count
     barrier()
     t_begin = time.time()
@@ -344,6 +358,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.ref_n)
 
+    faulthandler.cancel_dump_traceback_later()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": world,

@@ -273,6 +273,22 @@ struct NcclTransport : Transport {
   explicit NcclTransport(Engine& e, const ncclUniqueId& id) {
     CUDA_CHECK(cudaSetDevice(e.device()));
     NCCL_CHECK(NcclApi::get().CommInitRank(&comm, e.strip().world, id, e.strip().rank));
+    // Establish every point-to-point connection now, with one tiny symmetric exchange, instead of
+    // lazily inside the first iteration: connection setup is a rendezvous between the two ranks,
+    // and doing it here keeps it out of the stepping pipeline (and makes a transport problem show
+    // up at connect time, where the caller can time out, rather than as a stalled step).
+    StripState& s = e.strip_mut();
+    DevBuf<int> probe;
+    probe.alloc(2 * (size_t)s.world);
+    CUDA_CHECK(cudaMemsetAsync(probe.p, 0, 2 * s.world * sizeof(int), e.stream()));
+    NCCL_CHECK(NcclApi::get().GroupStart());
+    for (int r = 0; r < s.world; ++r) {
+      if (r == s.rank) continue;
+      NCCL_CHECK(NcclApi::get().Send(probe.p + r, sizeof(int), ncclChar, r, comm, e.stream()));
+      NCCL_CHECK(NcclApi::get().Recv(probe.p + s.world + r, sizeof(int), ncclChar, r, comm, e.stream()));
+    }
+    NCCL_CHECK(NcclApi::get().GroupEnd());
+    CUDA_CHECK(cudaStreamSynchronize(e.stream()));
   }
   ~NcclTransport() override {
     if (comm) NcclApi::get().CommDestroy(comm);

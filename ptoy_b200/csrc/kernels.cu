@@ -16,12 +16,6 @@
 //   gather_kernel    deterministic (stable) reorder of pos/vel/id + id->slot map
 #include "common.h"
 
-#ifndef PTOY_ROW_PREFETCH
-#define PTOY_ROW_PREFETCH 1
-#endif
-#ifndef PTOY_SCAN_UNROLL
-#define PTOY_SCAN_UNROLL 2
-#endif
 // resident CTAs per SM the stage kernels are compiled for (measured on B200: 40 registers win
 // without bonds, 48 with the bond partner prefetch)
 #ifndef PTOY_STAGE_MINB
@@ -364,22 +358,13 @@ __device__ __forceinline__ float2 particle_force(
       }
     };
     auto scan = [&](const float2* __restrict__ P, int q, int end) {
-#if PTOY_SCAN_UNROLL == 4
-      for (; q + 3 < end; q += 4) {
-        const float2 p0 = __ldg(P + q), p1 = __ldg(P + q + 1), p2 = __ldg(P + q + 2), p3 = __ldg(P + q + 3);
-        test(p0); test(p1); test(p2); test(p3);
-      }
-      for (; q < end; ++q) test(__ldg(P + q));
-#else
       for (; q + 1 < end; q += 2) {
         const float2 p0 = __ldg(P + q), p1 = __ldg(P + q + 1);
         test(p0);
         test(p1);
       }
       if (q < end) test(__ldg(P + q));
-#endif
     };
-#if PTOY_ROW_PREFETCH
     if (!(FEAT & kFeatStrips)) {
       // the three rows every particle needs: all six cell offsets are loaded before the first
       // scan; the rare extra rows (fractional position within the margin of a cell edge) follow
@@ -399,27 +384,33 @@ __device__ __forceinline__ float2 particle_force(
         const int* s2 = a.start + (Si + 2) * a.g.SJ;
         scan(X, __ldg(s2 + c_lo), __ldg(s2 + c_hi + 1));
       }
-    } else
-#endif
-    for (int R = r_lo; R <= r_hi; ++R) {
-      if (!(FEAT & kFeatStrips) || (R >= a.g.own_lo && R < a.g.own_hi)) {
-        const int base = R * a.g.SJ;
-        const int beg = __ldg(a.start + base + c_lo), end = __ldg(a.start + base + c_hi + 1);
-        if (R == Si) {
-          scan(X, beg, slot);
-          scan(X, slot + 1, end);
+    } else {
+      // strips: the same row order (so that N strips sum in the order one GPU does); a row outside
+      // the owned range is a row of the neighbouring strip, served from its ghost slices
+      auto scan_row = [&](int R) {
+        if (R >= a.g.own_lo && R < a.g.own_hi) {
+          const int base = R * a.g.SJ;
+          const int beg = __ldg(a.start + base + c_lo), end = __ldg(a.start + base + c_hi + 1);
+          if (R == Si) {
+            scan(X, beg, slot);
+            scan(X, slot + 1, end);
+          } else {
+            scan(X, beg, end);
+          }
         } else {
-          scan(X, beg, end);
+          const int side = R >= a.g.own_hi;
+          const int* gs = a.gstart[side];
+          if (gs == nullptr) return;
+          const int base = (R - (side ? a.g.own_hi : a.g.own_lo - 2)) * a.g.SJ;
+          const int g0 = __ldg(gs);
+          scan(a.gpos[side], __ldg(gs + base + c_lo) - g0, __ldg(gs + base + c_hi + 1) - g0);
         }
-      } else {
-        // a row of the neighbouring strip: its particles and cell offsets arrive as ghost slices
-        const int side = R >= a.g.own_hi;
-        const int* gs = a.gstart[side];
-        if (gs == nullptr) continue;
-        const int base = (R - (side ? a.g.own_hi : a.g.own_lo - 2)) * a.g.SJ;
-        const int g0 = __ldg(gs);
-        scan(a.gpos[side], __ldg(gs + base + c_lo) - g0, __ldg(gs + base + c_hi + 1) - g0);
-      }
+      };
+      scan_row(Si - 1);
+      scan_row(Si);
+      scan_row(Si + 1);
+      if (r_lo < Si - 1) scan_row(Si - 2);
+      if (r_hi > Si + 1) scan_row(Si + 2);
     }
     for (int k = 0; k < nq; ++k) eval_hit(ph, hq.dx[k][t], hq.dy[k][t], fx, fy);
   }

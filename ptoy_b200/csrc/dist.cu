@@ -273,7 +273,7 @@ struct NcclTransport : Transport {
   explicit NcclTransport(Engine& e, const ncclUniqueId& id) {
     CUDA_CHECK(cudaSetDevice(e.device()));
     NCCL_CHECK(NcclApi::get().CommInitRank(&comm, e.strip().world, id, e.strip().rank));
-    // Establish every point-to-point connection now, with one tiny symmetric exchange, instead of
+    // Establish the neighbour connections now, with one tiny symmetric exchange, instead of
     // lazily inside the first iteration: connection setup is a rendezvous between the two ranks,
     // and doing it here keeps it out of the stepping pipeline (and makes a transport problem show
     // up at connect time, where the caller can time out, rather than as a stalled step).
@@ -283,7 +283,7 @@ struct NcclTransport : Transport {
     CUDA_CHECK(cudaMemsetAsync(probe.p, 0, 2 * s.world * sizeof(int), e.stream()));
     NCCL_CHECK(NcclApi::get().GroupStart());
     for (int r = 0; r < s.world; ++r) {
-      if (r == s.rank) continue;
+      if (r != s.rank - 1 && r != s.rank + 1) continue;  // the neighbours: all a portal-free scene ever talks to
       NCCL_CHECK(NcclApi::get().Send(probe.p + r, sizeof(int), ncclChar, r, comm, e.stream()));
       NCCL_CHECK(NcclApi::get().Recv(probe.p + s.world + r, sizeof(int), ncclChar, r, comm, e.stream()));
     }
@@ -317,9 +317,14 @@ struct NcclTransport : Transport {
   void migrants(Engine& e) override {
     StripState& s = e.strip_mut();
     const size_t st = (size_t)mig_stride(s.out_cap);
+    // Without portals a particle moves less than one sub-row per iteration, so it can only enter
+    // an adjacent strip: exchange with the two neighbours.  With portals a teleport can land on
+    // any strip: all-to-all.  (Every rank holds the same portal list, so both ends agree.)
+    const bool all_to_all = e.has_portals();
     NCCL_CHECK(NcclApi::get().GroupStart());
     for (int r = 0; r < s.world; ++r) {
       if (r == s.rank) continue;
+      if (!all_to_all && r != s.rank - 1 && r != s.rank + 1) continue;
       NCCL_CHECK(NcclApi::get().Send(s.outbox.p + r * st, st, ncclChar, r, comm, e.stream()));
       NCCL_CHECK(NcclApi::get().Recv(s.inbox.p + r * st, st, ncclChar, r, comm, e.stream()));
     }

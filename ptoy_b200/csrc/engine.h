@@ -123,6 +123,7 @@ class Engine {
   void phase_ghost_map();      // neighbours' boundary ids -> id -> slot map (bonds across strips)
   void phase_stage1();
   bool has_bonds() const { return !bonds_.empty(); }
+  bool has_portals() const { return !portals_.empty(); }
   void phase_stage2();
   void phase_reorder();        // arrivals + reorder
   void phase_end();            // snapshot, time

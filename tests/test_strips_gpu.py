@@ -37,7 +37,7 @@ def strips(sc, steps, world, col_begin=None, setup=None):
     return out
 
 
-@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_strips_equal_single_engine_moving_particles(world):
     # velocities up to 4: ~1 % of the particles change sub-row per step, so 60 steps push
     # thousands across the strip boundaries in both directions

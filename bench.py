@@ -53,15 +53,45 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region: NVML in a
+    background thread (every 5 ms); `nvidia-smi -lms` as a fallback when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.stop_flag, self.th = None, False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            R = pynvml
+            bits = {"hw_slowdown": getattr(R, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(R, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(R, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(R, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.time(), sm, mx, [k for k, v in bits.items() if rs & v]))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.nvml = pynvml
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
@@ -72,40 +102,40 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                self.rows.append((time.time(), float(f[0]), float(f[1]),
+                                  [nm for k, nm in enumerate(names) if f[3 + k].lower().startswith("active")]))
+            except ValueError:
+                continue
 
     def stop(self, window=None):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.th:
+            self.th.join(timeout=1)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"],
+                    "samples": 0}
         rows = self.rows
         where = "warm-up + timed region + per-kernel pass (all under load)"
         if window is not None:
             inside = [r for r in rows if window[0] <= r[0] <= window[1]]
             if len(inside) >= 2:
                 rows, where = inside, "timed region"
-        for _, r in rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": where}
+        reasons = sorted({x for r in rows for x in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
+                "reasons": reasons, "samples": len(rows), "window": where,
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 
@@ -176,7 +206,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--particles", dest="n", type=int, default=16_000_000, help="particles per GPU")
+    ap.add_argument("--particles", dest="n", type=int, default=None,
+                    help="particles per GPU (default: 16M at N=1 = configs[2]; 32M at N>1 = configs[4], 256M on 8 GPUs)")
     ap.add_argument("--ref-particles", dest="ref_n", type=int, default=1_000_000, help="particles of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -196,6 +227,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.n is None:
+        args.n = 16_000_000 if world == 1 else 32_000_000
     # a stalled collective must not hold the box: dump the Python stacks and exit after a while
     faulthandler.dump_traceback_later(int(os.environ.get("PTOY_WATCHDOG_S", "420")), exit=True)
 

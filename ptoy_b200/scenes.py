@@ -157,7 +157,7 @@ def reference_grid(domain):
 
 def strip_scene(n_per_rank, rank, world, pitch_over_r=2.2, jitter_over_r=0.025, seed=1234, aspect=None):
     """Weak-scaling scene (configs[4]/[5] style dense packing): ONE global hex-packed scene of
-    world * n_per_rank particles whose width grows with `world`; returns the particles of the
+    about world * n_per_rank particles in a roughly square domain; returns the particles of the
     block columns that `rank` owns under the equal-column partition, with global ids.
 
     The x direction is the slow block index (blocks.h:160), i.e. the direction strips are cut in.
@@ -166,10 +166,12 @@ def strip_scene(n_per_rank, rank, world, pitch_over_r=2.2, jitter_over_r=0.025, 
     r = float(R)
     pitch = pitch_over_r * r
     row_h = pitch * np.sqrt(3.0) / 2.0
-    # strip aspect: height fixed by one rank's share, width proportional to world
-    h1 = np.sqrt(n_per_rank * pitch * row_h * (aspect or 0.75))
+    # the GLOBAL domain stays roughly square (aspect = width / height) so that float32 coordinates
+    # keep their resolution at 256M particles; strips get narrower as world grows
+    n_target = n_per_rank * world
+    h1 = np.sqrt(n_target * pitch * row_h / (aspect or 1.0))
     rows = max(4, int(round(h1 / row_h)))
-    cols_per_rank = int(np.ceil(n_per_rank / rows))
+    cols_per_rank = int(np.ceil(n_target / rows / world))
     cols = cols_per_rank * world
     n_global = rows * cols
     bx = -1.0 + 2 * r + pitch * (cols + 0.5)

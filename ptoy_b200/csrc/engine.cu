@@ -708,7 +708,7 @@ StageArgs Engine::make_stage_args(int stage) {
   a.n_sides = has_portal_tables_ ? (int)portals_.size() * 2 : 0;
   a.sides = sides_.p; a.pblk_ptr = pblk_ptr_.p; a.pblk = pblk_.p;
   a.blk_flags = has_portal_tables_ ? blk_flags_.p : nullptr;
-  a.need_id = a.has_frozen || a.has_bonds || pick_enabled_ || strip_.world > 1;
+  a.need_id = a.has_frozen || a.has_bonds || pick_enabled_;
   a.force_out = nullptr;
   a.newcell = newcell_.p; a.cnt = cnt_.p;
   a.cell = cell_[cur_].p;

@@ -365,7 +365,9 @@ __device__ __forceinline__ float2 particle_force(
       }
       if (q < end) test(__ldg(P + q));
     };
-    if (!(FEAT & kFeatStrips)) {
+    if (!(FEAT & kFeatStrips) || (r_lo >= a.g.own_lo && r_hi < a.g.own_hi)) {
+      // (strips: taken by every particle whose search rows are all owned — all but the two
+      // boundary rows on each side)
       // the three rows every particle needs: all six cell offsets are loaded before the first
       // scan; the rare extra rows (fractional position within the margin of a cell edge) follow
       const int* sp = a.start + (Si - 1) * a.g.SJ;
@@ -602,8 +604,8 @@ __device__ __forceinline__ void teleport(const A& a, int blk, float2& x, float2&
 // blocks::SortParticles).  A particle whose new sub-row belongs to another strip is put into
 // that strip's outbox (with its old slot, which fixes its place in the receiver's stable order)
 // and leaves this strip through the trash bin.
-__device__ __forceinline__ void key_and_count(const GridDev& g, const DistDev& d, float2 x, float2 v, int pid,
-                                              int slot, unsigned* newcell, int* cnt) {
+__device__ __forceinline__ void key_and_count(const GridDev& g, const DistDev& d, float2 x, float2 v,
+                                              const int* __restrict__ id, int slot, unsigned* newcell, int* cnt) {
   const Cell c = cell_of_fast(g, x);
   bool migrant;
   const unsigned pc = pack_cell(g, c, migrant);
@@ -615,7 +617,7 @@ __device__ __forceinline__ void key_and_count(const GridDev& g, const DistDev& d
     if (k < d.out_cap) {
       reinterpret_cast<float2*>(blk + mig_off_pos())[k] = x;
       reinterpret_cast<float2*>(blk + mig_off_vel(d.out_cap))[k] = v;
-      reinterpret_cast<int*>(blk + mig_off_id(d.out_cap))[k] = pid;
+      reinterpret_cast<int*>(blk + mig_off_id(d.out_cap))[k] = id[slot];
       reinterpret_cast<int*>(blk + mig_off_tag(d.out_cap))[k] = slot;
     }
   }
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, (FEAT & kFeatBonds) ? PTOY_STAGE_MIN
     float2 vn = make_float2(vx, vy);
     if (a.do_tail) {
       if ((FEAT & kFeatPortals) && (flags & 1u)) teleport(a, blk, xn, vn);
-      key_and_count(a.g, a.dist, xn, vn, pid, i, a.newcell, a.cnt);
+      key_and_count(a.g, a.dist, xn, vn, a.id, i, a.newcell, a.cnt);
     }
     a.pos_out[i] = xn;
     a.vel_out[i] = vn;
@@ -696,7 +698,7 @@ __global__ void __launch_bounds__(kThreads) tail_kernel(const __grid_constant__ 
       a.vel[i] = v;
     }
   }
-  key_and_count(a.g, a.dist, x, a.vel[i], a.id[i], i, a.newcell, a.cnt);
+  key_and_count(a.g, a.dist, x, a.vel[i], a.id, i, a.newcell, a.cnt);
 }
 
 // ---------------------------------------------------------------------------------

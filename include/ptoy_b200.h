@@ -82,6 +82,18 @@ int ptoy_upload_state(ptoy_engine* h, const float* pos_xy, const float* vel_xy,
 int ptoy_download_state(ptoy_engine* h, float* pos_xy, float* vel_xy, int32_t* id,
                         size_t cap, size_t* n);
 
+/* Pipelined forms of the two calls above, for streaming independent batches through several
+ * handles (every handle owns a CUDA stream): the copies and the re-binning are only ENQUEUED.
+ * The host buffers must be pinned and stay untouched until ptoy_synchronize(h) returns.
+ * max_id = largest id in the batch (the synchronous form scans for it).  The async upload does
+ * not run CheckBonds (particles.cpp:205-215) against the state it replaces.
+ * ptoy_download_state_async copies min(cap, upper bound of the live count) entries;
+ * ptoy_downloaded_count returns the exact live count once ptoy_synchronize has returned. */
+int ptoy_upload_state_async(ptoy_engine* h, const float* pos_xy, const float* vel_xy,
+                            const int32_t* id, size_t n, int32_t max_id);
+int ptoy_download_state_async(ptoy_engine* h, float* pos_xy, float* vel_xy, int32_t* id, size_t cap);
+int ptoy_downloaded_count(ptoy_engine* h, size_t* n);
+
 /* ---- stepping --------------------------------------------------------------------- */
 
 /* Particles::step(time_target, quit=false) (particles.cpp:93-203): iterate

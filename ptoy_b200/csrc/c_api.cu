@@ -88,6 +88,16 @@ int ptoy_add_particles_device(ptoy_engine* h, const float* pos, const float* vel
 int ptoy_upload_state(ptoy_engine* h, const float* pos, const float* vel, const int32_t* id, size_t n) {
   PTOY_TRY(h, E.upload_state(pos, vel, id, n))
 }
+int ptoy_upload_state_async(ptoy_engine* h, const float* pos, const float* vel, const int32_t* id, size_t n,
+                            int32_t max_id) {
+  PTOY_TRY(h, E.upload_state_async(pos, vel, id, n, max_id))
+}
+int ptoy_download_state_async(ptoy_engine* h, float* pos, float* vel, int32_t* id, size_t cap) {
+  PTOY_TRY(h, E.download_state_async(pos, vel, id, cap))
+}
+int ptoy_downloaded_count(ptoy_engine* h, size_t* n) {
+  PTOY_TRY(h, *n = E.downloaded_count())
+}
 int ptoy_download_state(ptoy_engine* h, float* pos, float* vel, int32_t* id, size_t cap, size_t* n) {
   PTOY_TRY(h, *n = E.download_state(pos, vel, id, cap))
 }

@@ -663,6 +663,41 @@ void Engine::upload_state(const float* pos, const float* vel, const int32_t* id,
   add_particles(pos, vel, id, n, false);
 }
 
+// Pipelined forms: everything is enqueued on this engine's stream and nothing waits, so
+// several handles (one stream each) overlap upload, stepping and download of independent
+// batches.  n_old = 0 and the id bound come from the caller instead of a device read / host scan.
+void Engine::upload_state_async(const float* pos, const float* vel, const int32_t* id, size_t n, int32_t max_id) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  if (max_id < 0 && n) throw Error(-2, "upload_state_async needs the largest id of the batch");
+  if (n >= (1ull << 31) - 1024) throw Error(-4, "more than 2^31 particles");
+  sync_env();
+  slot_map_valid_ = false;
+  if (n) {
+    ensure_capacity(n + (size_t)arrivals_bound());
+    ensure_id_capacity((size_t)max_id + 1);
+  }
+  if (slot_of_id_.p && !bonds_.empty()) { launch_fill_i32(slot_of_id_.p, -1, id_cap_ + 1, stream_); ++launches_; }
+  launch_fill_i32(&ctr_.p->n_cur, (int)n, 1, stream_);
+  ++launches_;
+  n_bound_ = (int)n;
+  if (!n) return;
+  CUDA_CHECK(cudaMemcpyAsync(pos_[cur_].p, pos, n * sizeof(float2), cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(vel_[cur_].p, vel, n * sizeof(float2), cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(id_[cur_].p, id, n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  rekey_and_reorder(0, false);
+}
+
+void Engine::download_state_async(float* pos, float* vel, int32_t* id, size_t cap) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  const size_t n = std::min(cap, (size_t)std::max(n_bound_, 0));
+  if (n) {
+    if (pos) CUDA_CHECK(cudaMemcpyAsync(pos, pos_[cur_].p, n * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
+    if (vel) CUDA_CHECK(cudaMemcpyAsync(vel, vel_[cur_].p, n * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
+    if (id) CUDA_CHECK(cudaMemcpyAsync(id, id_[cur_].p, n * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(h_ctr_, ctr_.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream_));
+}
+
 size_t Engine::download_state(float* pos, float* vel, int32_t* id, size_t cap) {
   read_counters();
   const size_t n = std::min(cap, (size_t)h_ctr_->n_cur);

@@ -67,6 +67,9 @@ class Engine {
   void add_particles(const float* pos, const float* vel, const int32_t* id, size_t n, bool on_device);
   void upload_state(const float* pos, const float* vel, const int32_t* id, size_t n);
   size_t download_state(float* pos, float* vel, int32_t* id, size_t cap);
+  void upload_state_async(const float* pos, const float* vel, const int32_t* id, size_t n, int32_t max_id);
+  void download_state_async(float* pos, float* vel, int32_t* id, size_t cap);
+  size_t downloaded_count() const { return (size_t)h_ctr_->n_cur; }
 
   // stepping
   void step_to(float time_target);

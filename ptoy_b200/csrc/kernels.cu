@@ -800,23 +800,30 @@ __global__ void __launch_bounds__(kThreads) fill_kernel(const __grid_constant__ 
   const int i = blockIdx.x * kThreads + threadIdx.x;
   if (i >= a.ctr->n_cur + a.ctr->n_arrived) return;
   const int key = key_of_packed(a.newcell[i], a.SJ, a.ncell);
-  // counting down leaves the histogram all-zero again for the next iteration
-  const int r = atomicSub(a.cnt + key, 1) - 1;
-  a.order[a.start[key] + r] = i;
+  // counting down leaves the histogram all-zero again for the next iteration; the first atomic
+  // served takes the first slot of the run, so that the usual service order (ascending old
+  // slot) already is the stable order gather_kernel wants
+  const int left = atomicSub(a.cnt + key, 1);
+  a.order[a.start[key + 1] - left] = i;
 }
 
 // New slot k receives the particle with the (k - start[c])-th smallest OLD slot among
 // the particles of its sub-cell c: the result is the stable sort by key, independent of
-// the order in which fill_kernel's atomics were served.
-__global__ void __launch_bounds__(kThreads) gather_kernel(const __grid_constant__ ReorderArgs a) {
+// the order in which fill_kernel's atomics were served.  The payload of the particle
+// fill_kernel put at k is loaded before that is checked (it is the right one unless the
+// atomics of a shared cell were served out of order).
+__global__ void __launch_bounds__(kThreads, 8) gather_kernel(const __grid_constant__ ReorderArgs a) {
   const int k = blockIdx.x * kThreads + threadIdx.x;
   if (k >= a.ctr->n_total) return;
-  int src = a.order[k];
+  const int src0 = a.order[k];
   if (k >= a.ctr->n_next) {  // left the grid: removed (blocks.h:230-232)
-    if (a.slot_of_id) a.slot_of_id[a.id_in[src]] = -1;
+    if (a.slot_of_id) a.slot_of_id[a.id_in[src0]] = -1;
     return;
   }
-  const unsigned pc = a.newcell[src];
+  const unsigned pc = a.newcell[src0];
+  float2 p = a.pos_in[src0];
+  float2 v = a.vel_in[src0];
+  int pid = a.id_in[src0];
   const int c = key_of_packed(pc, a.SJ, a.ncell);
   const int beg = a.start[c], end = a.start[c + 1];
   if (end - beg > 1) {
@@ -825,17 +832,24 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const __grid_constant_
     auto vkey = [&](int i) -> unsigned long long {
       return i < n_loc ? ((unsigned long long)a.rank << 32) | (unsigned)i : a.arr_vkey[i - n_loc];
     };
-    for (int e = beg; e < end; ++e) {
-      const int cand = a.order[e];
+    auto rank_of = [&](int cand) -> int {
       const unsigned long long ck = vkey(cand);
       int smaller = 0;
       for (int e2 = beg; e2 < end; ++e2) smaller += (vkey(a.order[e2]) < ck);
-      if (smaller == want) { src = cand; break; }
+      return smaller;
+    };
+    if (rank_of(src0) != want) {
+      for (int e = beg; e < end; ++e) {
+        const int cand = a.order[e];
+        if (cand != src0 && rank_of(cand) == want) {
+          p = a.pos_in[cand]; v = a.vel_in[cand]; pid = a.id_in[cand];
+          break;
+        }
+      }
     }
   }
-  a.pos_out[k] = a.pos_in[src];
-  a.vel_out[k] = a.vel_in[src];
-  const int pid = a.id_in[src];
+  a.pos_out[k] = p;
+  a.vel_out[k] = v;
   a.id_out[k] = pid;
   a.cell_out[k] = pc;
   if (a.slot_of_id) a.slot_of_id[pid] = k;

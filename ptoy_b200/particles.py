@@ -36,6 +36,9 @@ SIGNATURES = {
     "ptoy_add_particles_device": [_vp, _vp, _vp, _sz],
     "ptoy_upload_state": [_vp, _vp, _vp, _sz],
     "ptoy_download_state": [_vp, _vp, _vp, _sz, _szp],
+    "ptoy_upload_state_async": [_vp, _vp, _vp, _sz, C.c_int32],
+    "ptoy_download_state_async": [_vp, _vp, _vp, _sz],
+    "ptoy_downloaded_count": [_szp],
     "ptoy_step": [_f],
     "ptoy_step_n": [_i],
     "ptoy_synchronize": [],
@@ -332,6 +335,22 @@ class Particles:
         """Copy the live state (engine order) into the given host arrays; returns the count."""
         n = C.c_size_t()
         self._call("ptoy_download_state", _ptr(pos), _ptr(vel), _ptr(ids), len(pos), C.byref(n))
+        return n.value
+
+    def upload_state_async(self, pos, vel, ids, max_id):
+        """Enqueue upload_state on this engine's stream (pinned arrays; nothing waits)."""
+        assert pos.dtype == np.float32 and vel.dtype == np.float32 and ids.dtype == np.int32
+        self._call("ptoy_upload_state_async", pos.ctypes.data, vel.ctypes.data, ids.ctypes.data, len(ids),
+                   int(max_id))
+
+    def download_state_async(self, pos, vel, ids):
+        """Enqueue download_state; the arrays are valid after synchronize()."""
+        self._call("ptoy_download_state_async", _ptr(pos), _ptr(vel), _ptr(ids), len(pos))
+
+    @property
+    def downloaded_count(self):
+        n = C.c_size_t()
+        self._call("ptoy_downloaded_count", C.byref(n))
         return n.value
 
     def set_bonds(self, pairs):

@@ -353,6 +353,58 @@ def test_determinism_and_incremental_add():
         assert np.array_equal(outs[a][2], outs[b][2])
 
 
+def test_pipelined_upload_step_download_equals_the_synchronous_calls():
+    """ptoy_upload_state_async / ptoy_download_state_async on several handles in flight give the
+    same bits as ptoy_upload_state / ptoy_step_n / ptoy_download_state on one handle."""
+    import torch
+    sc = golden_scenes()["bonded3k"][0]
+
+    def pinned(n):
+        return (torch.empty((n, 2), dtype=torch.float32).pin_memory().numpy(),
+                torch.empty((n, 2), dtype=torch.float32).pin_memory().numpy(),
+                torch.empty((n,), dtype=torch.int32).pin_memory().numpy())
+
+    # three different batches: the scene advanced by 0, 3 and 6 iterations
+    src = gpu(default_scene=False)
+    scenes.load_into(src, sc)
+    batches = []
+    for _ in range(3):
+        b = pinned(sc.n)
+        assert src.download_state(*b) == sc.n
+        batches.append(b)
+        src.step_n(3)
+
+    ref = []
+    g = gpu(default_scene=False)
+    scenes.load_into(g, sc)
+    for b in batches:
+        out = pinned(sc.n)
+        for _ in range(2):                                # two round trips per batch
+            g.upload_state(*(b if _ == 0 else out))
+            g.step_n(1)
+            assert g.download_state(*out) == sc.n
+        ref.append(out)
+
+    engines = []
+    for b in batches:
+        e = gpu(default_scene=False)
+        scenes.load_into(e, sc)
+        engines.append(e)
+    work = [tuple(a.copy() for a in b) for b in batches]
+    work = [tuple(torch.from_numpy(a).pin_memory().numpy() for a in b) for b in work]
+    for _ in range(2):
+        for e, b in zip(engines, work):
+            e.synchronize()
+            e.upload_state_async(b[0], b[1], b[2], sc.n - 1)
+            e.step_n(1)
+            e.download_state_async(*b)
+    for e, b, r in zip(engines, work, ref):
+        e.synchronize()
+        assert e.downloaded_count == sc.n and e.error_flags == 0
+        assert np.array_equal(b[2], r[2])
+        assert bits_equal(b[0], r[0]) and bits_equal(b[1], r[1])
+
+
 # --------------------------------------------------------------------------- full size
 def _numpy_find_block(pos, grid, dims):
     """blocks::FindBlock (blocks.h:155-163) in float32 numpy."""

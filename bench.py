@@ -141,16 +141,41 @@ class ClockSampler:
 
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use every host
+    core it can, so set the OpenMP thread count back (environment for libraries loaded later,
+    omp_set_num_threads for a libgomp that is already initialised)."""
+    import ctypes
+    n = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU Particles::step on the box's host cores."""
-    from oracle import port, ref
-    from ptoy_b200 import scenes
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
+    from oracle import port, ref
+    from ptoy_b200 import scenes
     n = args.ref_n
     variants = [v for v in ("omp", "avx_omp") if ref.available(v)]
-    sc = scenes.config3(n)
+    # the same workload as the CUDA arm at this N (see main()): configs[2] at N=1, the dense
+    # strip scene (one strip of it: the CPU reference has no decomposition) at N>1
+    if args.gpus == 1:
+        sc = scenes.config3(n)
+        workload = "configs[2]: 16M particles, ~4 bonds/particle, 1% frozen (bounded CPU sample)"
+        gen = "configs[2] generator at n=%d (pitch 2.02r hex, ~4 bonds/particle, 1%% frozen)" % n
+    else:
+        sc = scenes.strip_scene(n, 0, 1)
+        workload = "configs[4]: dense hex packing pitch 2.2r, pair+gravity+walls (bounded CPU sample)"
+        gen = "strip-scene generator at n=%d (pitch 2.2r hex, no bonds)" % sc.n
+    n = sc.n
     best = None
     for v in variants or ["port"]:
         o = ref.RefParticles(v) if v != "port" else port.PortParticles()
@@ -166,15 +191,13 @@ def run_reference(args):
         o.close()
     rate, v, threads, spstep = best
     kind = "port" if v == "port" else "reference"
-    sample = (f"configs[2] generator at n={n} (pitch 2.02r hex, ~4 bonds/particle, 1% frozen), "
-              f"{args.steps_ref} iterations after {args.warmup_ref} warm-up, build={v}")
+    sample = f"{gen}, {args.steps_ref} iterations after {args.warmup_ref} warm-up, build={v}"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "particle-updates/s",
         "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref,
         "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[2]: 16M particles, ~4 bonds/particle, 1% frozen (bounded CPU sample)",
-                   "sample_particles": n},
+        "config": {"workload": workload, "sample_particles": n},
         "cpu_baseline": {"value": rate, "unit": "particle-updates/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -182,6 +205,7 @@ def run_reference(args):
 
 
 def cpu_baseline(n, steps=3, warmup=1):
+    use_all_host_threads()
     from oracle import port, ref
     from ptoy_b200 import scenes
     sc = scenes.config3(n)

@@ -750,28 +750,37 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(
   const int block_total = s_warp[kThreads / 32 - 1];
   const int excl_in_block = incl - tsum + (warp ? s_warp[warp - 1] : 0);
 
-  // publish aggregate / look back.  state = (epoch*4 + flag) << 32 | value
+  // publish aggregate / look back.  state = (epoch*4 + flag) << 32 | value; flag 1 = this tile's
+  // total, flag 2 = inclusive prefix.  Warp 0 looks at 32 predecessors per round: lane l reads
+  // tile t - l, the nearest one that already holds an inclusive prefix ends the walk.
   const unsigned long long tag = (unsigned long long)epoch << 2;
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     volatile unsigned long long* st = tile_state;
+    int prefix = 0;
     if (tile == 0) {
-      st[0] = ((tag | 2ull) << 32) | (unsigned)block_total;
-      s_prefix = 0;
+      if (lane == 0) st[0] = ((tag | 2ull) << 32) | (unsigned)block_total;
     } else {
-      st[tile] = ((tag | 1ull) << 32) | (unsigned)block_total;
-      int prefix = 0;
+      if (lane == 0) st[tile] = ((tag | 1ull) << 32) | (unsigned)block_total;
       int t = tile - 1;
       while (true) {
-        const unsigned long long s = st[t];
-        const unsigned long long f = s >> 32;
-        if (f == (tag | 2ull)) { prefix += (int)(unsigned)s; break; }
-        if (f == (tag | 1ull)) { prefix += (int)(unsigned)s; --t; continue; }
-        // not published yet: spin (tickets are handed out in order, so tile t is running)
+        const int idx = t - lane;
+        unsigned long long sv = (tag | 2ull) << 32;  // before the first tile: inclusive prefix 0
+        if (idx >= 0) {
+          // not published yet: spin (tickets are handed out in order, so tile idx is running)
+          do { sv = st[idx]; } while ((sv >> 32) != (tag | 1ull) && (sv >> 32) != (tag | 2ull));
+        }
+        const unsigned done = __ballot_sync(0xffffffffu, (sv >> 32) == (tag | 2ull));
+        const int first = done ? __ffs(done) - 1 : 31;
+        int c = lane <= first ? (int)(unsigned)sv : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        prefix += c;
+        if (done) break;
+        t -= 32;
       }
-      st[tile] = ((tag | 2ull) << 32) | (unsigned)(prefix + block_total);
-      s_prefix = prefix;
+      if (lane == 0) st[tile] = ((tag | 2ull) << 32) | (unsigned)(prefix + block_total);
     }
-    __threadfence();
+    if (lane == 0) s_prefix = prefix;
   }
   __syncthreads();
   const int e0 = s_prefix + excl_in_block;

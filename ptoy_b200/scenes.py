@@ -155,13 +155,21 @@ def reference_grid(domain):
     return float(ax), float(ay), float(bx), float(by), di, dj
 
 
-def strip_scene(n_per_rank, rank, world, pitch_over_r=2.2, jitter_over_r=0.025, seed=1234, aspect=None):
+def strip_scene(n_per_rank, rank, world, pitch_over_r=2.2, jitter_over_r=0.025, seed=1234, aspect=None,
+                bonds=False, bond_margin_cols=8):
     """Weak-scaling scene (configs[4]/[5] style dense packing): ONE global hex-packed scene of
     about world * n_per_rank particles in a roughly square domain; returns the particles of the
     block columns that `rank` owns under the equal-column partition, with global ids.
 
     The x direction is the slow block index (blocks.h:160), i.e. the direction strips are cut in.
-    Attributes: n_global, col_begin (the partition to pass to configure_strips), dims."""
+    Attributes: n_global, col_begin (the partition to pass to configure_strips), dims.
+
+    bonds=True adds the configs[2] features to the GLOBAL scene: each of the 3 forward
+    hex-neighbour edges kept with p=2/3 and 1 % frozen ids, both decided by a hash of the global
+    id, so every rank derives the same network without generating all of it.  `bonds` then holds
+    the directed pairs whose first id lies in this rank's lattice columns widened by
+    `bond_margin_cols` (the rows a rank can need while particles stay within that margin of
+    their strip), `frozen` the frozen ids of the same columns."""
     from .particles import partition_columns
     r = float(R)
     pitch = pitch_over_r * r
@@ -202,7 +210,51 @@ def strip_scene(n_per_rank, rank, world, pitch_over_r=2.2, jitter_over_r=0.025, 
     sc = Scene(domain, pos[mine], np.zeros((int(mine.sum()), 2), np.float32), ids[mine].astype(np.int32),
                name=f"strip{rank}of{world}x{n_per_rank}")
     sc.n_global, sc.col_begin, sc.dims = int(n_global), cb, (di, dj)
+    sc.lattice = (rows, cols)
+    if bonds:
+        c_lo, c_hi = max(0, i_lo - bond_margin_cols), min(cols, i_hi + bond_margin_cols)
+        sc.bonds = hashed_lattice_bonds(rows, cols, c_lo, c_hi, seed=seed + 99)
+        ci, cj = np.meshgrid(np.arange(c_lo, c_hi, dtype=np.int64), np.arange(rows, dtype=np.int64))
+        cid = np.sort((cj * cols + ci).ravel())
+        sc.frozen = cid[_hash01(cid * 4 + 3, seed + 99) < 0.01].astype(np.int32)
+        sc.name += "+bonds"
     return sc
+
+
+def _hash01(key, seed):
+    """Deterministic uniform [0, 1) per integer key (splitmix64 finaliser)."""
+    z = (np.asarray(key, dtype=np.uint64) + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def hashed_lattice_bonds(rows, cols, c_lo, c_hi, keep_prob=2.0 / 3.0, seed=99):
+    """Directed bond pairs (sorted, both directions stored like particles.cpp:493-494) of the
+    hashed hex-lattice network whose FIRST id lies in lattice columns [c_lo, c_hi); ids are
+    row-major over the global rows x cols lattice.  Edge (k, direction d) is kept iff
+    hash(3k+d) < keep_prob, so any column range gives a consistent cut of one global network."""
+    e_lo, e_hi = max(0, c_lo - 1), min(cols, c_hi + 1)       # forward edges reach one column over
+    ii, jj = np.meshgrid(np.arange(e_lo, e_hi, dtype=np.int64), np.arange(rows, dtype=np.int64))
+    i, j = ii.ravel(), jj.ravel()
+    k = j * cols + i
+    odd = (j % 2) == 1
+    up_ok = j + 1 < rows
+    cands = [(k + 1, i + 1 < cols),                                    # right
+             (k + cols, up_ok),                                        # up, same column
+             (np.where(odd, k + cols + 1, k + cols - 1),               # up-right (odd row) / up-left (even)
+              up_ok & np.where(odd, i + 1 < cols, i - 1 >= 0))]
+    pairs = []
+    for d, (nb, ok) in enumerate(cands):
+        m = ok & (_hash01(k * 4 + d, seed) < keep_prob)
+        pairs.append(np.stack([k[m], nb[m]], axis=1))
+    e = np.concatenate(pairs, axis=0)
+    both = np.concatenate([e, e[:, ::-1]], axis=0)
+    col_first = both[:, 0] % cols
+    both = both[(col_first >= c_lo) & (col_first < c_hi)]
+    order = np.lexsort((both[:, 1], both[:, 0]))
+    return np.ascontiguousarray(both[order].astype(np.int32))
 
 
 def config3(n=16_000_000, seed=1234):

@@ -16,6 +16,7 @@ namespace ptoy {
 
 constexpr int kMaxWalls = 16;
 constexpr int kThreads = 256;
+constexpr int kSlotNone = -1;   // id -> slot map entry of an id that is not stored (left the grid / never added)
 
 // Sub-cell grid.  S = floor(2*t) + 4 with t = fl(fl(x - A)/bs) exactly as
 // blocks::FindBlock computes it (blocks.h:156-158).
@@ -106,6 +107,8 @@ struct Counters {
   int removed_total;
   int max_sub_occupancy;
   int err_flags;
+  int n_fix;        // cells filed for fixup_kernel by the current reorder
+  unsigned dmax;    // float bits: largest per-component half-step drift measured by stage 1
 };
 
 struct StageArgs {
@@ -122,7 +125,7 @@ struct StageArgs {
   float2* pos_out;       // stage 2: x' (may alias pos)
   float2* vel_out;       // stage 2: v'
   const int* id;
-  const unsigned* cell;  // packed sub-cell (Si << 16 | Sj) of every sorted particle
+  const int* cell;       // sort key (local sub-row * SJ + sub-column) of every sorted particle
   const int* start;      // [ncell+2] exclusive prefix of sub-cell populations
   // ghost slices of the left (0) / right (1) neighbour strip for this stage: positions of its two
   // boundary sub-rows and the matching slice of its start[] (2*SJ+1 entries, absolute indices
@@ -130,7 +133,11 @@ struct StageArgs {
   const float2* gpos[2];
   const int* gstart[2];
   DistDev dist;
-  float margin;          // extra search margin in sub-cell units
+  float margin;          // extra search margin in sub-cell units; stage 2: its upper bound
+  // stage 2 of the tile kernels: margin = min(margin, margin_base + margin_scale * *dmax), where
+  // *dmax (float bits) is the largest per-component half-step drift stage 1 measured
+  float margin_base, margin_scale;
+  unsigned* dmax;
   // frozen_ as a bitmask over ids
   const uint32_t* frozen_bits;
   int has_frozen;
@@ -153,7 +160,7 @@ struct StageArgs {
   int need_id;
   // outputs
   float2* force_out;     // optional, by slot
-  unsigned* newcell;     // stage 2: packed sub-cell after the update (old slot order)
+  int* newcell;          // stage 2: sort key after the update (old slot order); ncell = trash bin
   int* cnt;              // stage 2: sub-cell histogram (RED)
   int do_tail;           // stage 2: teleport + key + histogram fused
   int write_state;       // 0 = forces only (debug)
@@ -174,7 +181,7 @@ struct TailArgs {  // standalone teleport + key pass (resize iterations, add_par
   DistDev dist;
   const int* id;
   int first;     // particles [first, n) are processed
-  unsigned* newcell;
+  int* newcell;
   int* cnt;
 };
 
@@ -182,17 +189,19 @@ struct ReorderArgs {
   const Counters* ctr;
   int ncell;
   int SJ;
-  const unsigned* newcell;
+  const int* newcell;
   const int* start;
-  int* cnt;          // histogram on entry; fill counts it down to zero
-  int* order;        // order[new slot] = old slot (nondeterministic within a cell)
+  int* cnt;          // all-zero on entry (the scan consumed the histogram) and on exit
+  int* tag;          // by new slot: old slot of a particle placed through the atomic counter
+  int* fixlist;      // cells whose members were placed through the atomic counter
+  int* n_fix;        // Counters::n_fix
   const float2* pos_in;
   const float2* vel_in;
   const int* id_in;
   float2* pos_out;
   float2* vel_out;
   int* id_out;
-  unsigned* cell_out;
+  int* cell_out;
   int* slot_of_id;   // optional
   // stable order across strips: locals sort as (rank, old slot), arrivals carry the (source
   // rank, old slot there) they had; equals the single-GPU stable order
@@ -209,7 +218,7 @@ struct ArrivalArgs {   // migrants received from every source rank -> appended b
   float2* pos;
   float2* vel;
   int* id;
-  unsigned* newcell;
+  int* newcell;
   int* cnt;
   unsigned long long* arr_vkey;
   int cap;
@@ -243,10 +252,10 @@ struct GhostMapArgs {
 // launchers (kernels.cu)
 void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s);
 void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s);
-void launch_scan(const int* cnt, int* start, int n_items, int ncell, unsigned long long* tile_state,
+void launch_scan(int* cnt, int* start, int n_items, int ncell, unsigned long long* tile_state,
                  int* ticket, unsigned epoch, Counters* ctr, cudaStream_t s);
-void launch_fill(const ReorderArgs& a, int n_bound, cudaStream_t s);
-void launch_gather(const ReorderArgs& a, int n_bound, cudaStream_t s);
+void launch_scatter(const ReorderArgs& a, int n_bound, cudaStream_t s);
+void launch_fixup(const ReorderArgs& a, int n_bound, cudaStream_t s);
 void launch_finalize(Counters* ctr, int* ticket, cudaStream_t s);
 void launch_arrivals(const ArrivalArgs& a, cudaStream_t s);
 void launch_ghost_pack(const GhostPackArgs& a, cudaStream_t s);

@@ -203,6 +203,9 @@ void Engine::alloc_cells() {
   margin1_ = std::ldexp(1.f, -19) + W * std::ldexp(1.f, -21) + grid_.tol;
   const float drift = kVelocityLimit * dt_ * 0.5f;
   margin2_ = margin1_ + 2.f * drift / (0.5f * bs_.x) * 1.001f + W * std::ldexp(1.f, -21);
+  // the same with the drift stage 1 measured instead of its bound (tile kernels)
+  margin2_base_ = margin1_ + W * std::ldexp(1.f, -21);
+  margin2_scale_ = 2.f / (0.5f * std::min(bs_.x, bs_.y)) * 1.001f;
   if (!(margin2_ < 0.5f)) throw Error(-2, "time step too large for the sub-cell search margin");
   if (strip_.world > 1) alloc_strip_buffers();
 }
@@ -222,6 +225,7 @@ void Engine::ensure_capacity(size_t n) {
   bslot_.alloc(nc * 8);
   for (int k = 0; k < 2; ++k) cell_[k].alloc(nc);  // rewritten by every reorder before use
   order_.alloc(nc);
+  fixlist_.alloc(nc);
   force_dbg_.release();
   cap_ = nc;
 }
@@ -732,6 +736,9 @@ StageArgs Engine::make_stage_args(int stage) {
   }
   a.dist = make_dist(true);
   a.margin = (stage == 1) ? margin1_ : margin2_;
+  a.margin_base = margin2_base_;
+  a.margin_scale = margin2_scale_;
+  a.dmax = strip_.world == 1 ? &ctr_.p->dmax : nullptr;  // (strips: the neighbours' drift is not known here)
   a.has_frozen = !frozen_.empty();
   a.frozen_bits = frozen_bits_.p;
   a.has_bonds = !bonds_.empty();
@@ -804,7 +811,9 @@ void Engine::reorder() {
   r.cell_out = cell_[cur_ ^ 1].p;
   r.start = start_.p;
   r.cnt = cnt_.p;
-  r.order = order_.p;
+  r.tag = order_.p;
+  r.fixlist = fixlist_.p;
+  r.n_fix = &ctr_.p->n_fix;
   r.pos_in = pos_[cur_].p; r.vel_in = vel_[cur_].p; r.id_in = id_[cur_].p;
   r.pos_out = pos_[cur_ ^ 1].p; r.vel_out = vel_[cur_ ^ 1].p; r.id_out = id_[cur_ ^ 1].p;
   r.rank = strip_.rank;
@@ -813,10 +822,10 @@ void Engine::reorder() {
   r.slot_of_id = keep_map ? slot_of_id_.p : nullptr;
   if (!keep_map) slot_map_valid_ = false;
   begin_timed(3);
-  launch_fill(r, n_bound_ + arrivals_bound(), stream_);
+  launch_scatter(r, n_bound_ + arrivals_bound(), stream_);
   end_timed();
   begin_timed(4);
-  launch_gather(r, n_bound_ + arrivals_bound(), stream_);
+  launch_fixup(r, n_bound_ + arrivals_bound(), stream_);
   end_timed();
   begin_timed(5);
   launch_finalize(ctr_.p, ticket_.p, stream_);
@@ -947,10 +956,7 @@ void Engine::step_to(float time_target) {
 }
 void Engine::step_n(int n) {
   CUDA_CHECK(cudaSetDevice(device_));
-  for (int i = 0; i < n; ++i) {
-    const float target = t_ + 0.25f * dt_;
-    while (t_ < target) iterate();
-  }
+  for (int i = 0; i < n; ++i) iterate();
 }
 void Engine::synchronize() {
   CUDA_CHECK(cudaSetDevice(device_));

@@ -189,8 +189,8 @@ class Engine {
   size_t id_cap_ = 0;
   int cur_ = 0;         // which of the ping-pong buffers holds the sorted state
   DevBuf<float2> pos_[2], vel_[2], pos_h_, vel_h_, force_dbg_;
-  DevBuf<int> id_[2], order_;
-  DevBuf<uint32_t> cell_[2], newcell_;
+  DevBuf<int> id_[2], order_, fixlist_;   // order_: reorder tags / scratch
+  DevBuf<int> cell_[2], newcell_;         // sort keys: of the sorted particles / after the update
   DevBuf<int> bslot_;            // [cap][8] bond partner slots + degree: stage 1 -> stage 2
   DevBuf<int> bond_ell_;         // [id_cap+1][8] bond table by id
   DevBuf<int> cnt_, start_;
@@ -213,7 +213,7 @@ class Engine {
   WallDev walls_dev_[kMaxWalls];
   float free_box_[4];
   float r2c_ = 0.f, v2c_ = 0.f;
-  float margin1_ = 0.f, margin2_ = 0.f;
+  float margin1_ = 0.f, margin2_ = 0.f, margin2_base_ = 0.f, margin2_scale_ = 0.f;
 
   // timing
   bool timing_ = false;

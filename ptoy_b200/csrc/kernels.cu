@@ -14,7 +14,10 @@
 //   scan_kernel      single-pass decoupled look-back exclusive scan of the histogram
 //   fill_kernel      counting-sort slot assignment
 //   gather_kernel    deterministic (stable) reorder of pos/vel/id + id->slot map
+#include <algorithm>
+
 #include "common.h"
+#include "device_math.cuh"
 
 // resident CTAs per SM the stage kernels are compiled for (measured on B200: 40 registers win
 // without bonds, 48 with the bond partner prefetch)
@@ -27,227 +30,6 @@
 
 namespace ptoy {
 
-// ---------------------------------------------------------------------------------
-// exact-rounding float helpers
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
-// (float)(1. / (double)x): double division then rounding to float equals the
-// correctly rounded float quotient (53 >= 2*24+2), i.e. __fdiv_rn(1, x).
-__device__ __forceinline__ float rcp_exact(float x) { return __frcp_rn(x); }
-// geometry.h:62-64  dot = v.x*x + v.y*y
-__device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) {
-  return fadd(fmul(ax, bx), fmul(ay, by));
-}
-// geometry.h:65-67  length = sqrt(x*x + y*y) (double sqrt of a float, rounded back:
-// identical to the correctly rounded float sqrt)
-__device__ __forceinline__ float len2(float x, float y) { return __fsqrt_rn(dot2(x, y, x, y)); }
-// r / R for the constant R = 2r = 0.04f (particles.cpp:729,733).  With y = fl(1/R) = 25 exactly,
-// q0 = fl(r*y), rem = fma(-q0, R, r), q1 = fma(rem, y, q0) is the correctly rounded quotient
-// (Markstein); checked exhaustively against r / R for every float r in [1e-30, 1e30]
-// (scripts/check_exact_tricks.c).  The fused multiply-adds are part of the division algorithm,
-// not contractions of reference operations.
-__device__ __forceinline__ float div_by_bondR(float r, float R, float y) {
-  const float q0 = __fmul_rn(r, y);
-  const float rem = __fmaf_rn(-q0, R, r);
-  return __fmaf_rn(rem, y, q0);
-}
-// std::max<float>(0, k) = (0 < k) ? k : 0   (NaN -> 0)
-__device__ __forceinline__ float max0(float k) { return (0.0f < k) ? k : 0.0f; }
-
-// ---------------------------------------------------------------------------------
-// binning (blocks::FindBlock, blocks.h:155-163) at sub-cell resolution
-// ---------------------------------------------------------------------------------
-struct Cell {
-  int Si, Sj;     // padded sub-cell row / column
-  float ui, uj;   // fractional position inside the sub-cell, [0,1)
-  bool valid;     // FindBlock != kBlockNone
-};
-
-__device__ __forceinline__ Cell cell_of(const GridDev& g, float2 p) {
-  Cell c;
-  const float tx = fdiv(fsub(p.x, g.Ax), g.bsx);
-  const float ty = fdiv(fsub(p.y, g.Ay), g.bsy);
-  // (int)t truncates toward zero: t in (-1,0) still maps to row/column 0
-  c.valid = (tx > -1.0f) && (tx < g.fdi) && (ty > -1.0f) && (ty < g.fdj);
-  const float wx = tx * 2.0f, wy = ty * 2.0f;  // exact
-  const float fx = floorf(wx), fy = floorf(wy);
-  c.Si = (int)fx + 4;
-  c.Sj = (int)fy + 4;
-  c.ui = wx - fx;  // exact
-  c.uj = wy - fy;
-  return c;
-}
-// Same result as cell_of() without the two IEEE divisions in the common case:
-// w~ = fl((x - A) * fl(2/bs)) differs from the exact w = 2*fl(fl(x - A)/bs) by less than
-// |w| * 2^-22, so floor(w~) == floor(w) unless w~ lies within g.tol (>= 2 * wmax * 2^-22) of an
-// integer; those few particles take the exact path.  (ui, uj are then approximate by < tol,
-// which the search margin absorbs.)
-__device__ __forceinline__ Cell cell_of_fast(const GridDev& g, float2 p) {
-  const float wx = fsub(p.x, g.Ax) * g.inv_hsx, wy = fsub(p.y, g.Ay) * g.inv_hsy;
-  const float fx = floorf(wx), fy = floorf(wy);
-  const float ux = wx - fx, uy = wy - fy;
-  const float hi = 1.0f - g.tol;
-  const bool safe = ux > g.tol && ux < hi && uy > g.tol && uy < hi &&
-                    fabsf(wx) < g.wmax && fabsf(wy) < g.wmax;  // false for NaN
-  if (!safe) return cell_of(g, p);
-  Cell c;
-  c.valid = fx >= -2.0f && fx < 2.0f * g.fdi && fy >= -2.0f && fy < 2.0f * g.fdj;
-  c.Si = (int)fx + 4;
-  c.Sj = (int)fy + 4;
-  c.ui = ux;
-  c.uj = uy;
-  return c;
-}
-__device__ __forceinline__ int block_of_s(const GridDev& g, int Si, int Sj) {
-  const int bi = max(0, (Si - 4) >> 1), bj = max(0, (Sj - 4) >> 1);
-  return bi * g.dj + bj;
-}
-__device__ __forceinline__ int block_of(const GridDev& g, const Cell& c) { return block_of_s(g, c.Si, c.Sj); }
-// packed sub-cell of a particle: Si << 16 | Sj ; kTrashCell = left the grid
-constexpr unsigned kTrashCell = 0xffffffffu;
-// local packed cell of a particle this strip keeps; kTrashCell if it left the grid or belongs
-// to another strip (`migrant`)
-__device__ __forceinline__ unsigned pack_cell(const GridDev& g, const Cell& c, bool& migrant) {
-  migrant = false;
-  if (!c.valid) return kTrashCell;
-  const int lr = c.Si - g.row0;
-  if (lr < g.own_lo || lr >= g.own_hi) { migrant = true; return kTrashCell; }
-  return ((unsigned)lr << 16) | (unsigned)c.Sj;
-}
-__device__ __forceinline__ int key_of_packed(unsigned p, int SJ, int ncell) {
-  return p == kTrashCell ? ncell : (int)(p >> 16) * SJ + (int)(p & 0xffffu);
-}
-// sub-rows / sub-columns (inclusive) that make up reference block `blk`
-__device__ __forceinline__ void block_extent(const GridDev& g, int blk, int& r0, int& r1, int& c0, int& c1) {
-  const int bi = blk / g.dj, bj = blk - bi * g.dj;
-  r0 = (bi == 0) ? 2 : 2 * bi + 4;
-  r1 = 2 * bi + 5;
-  c0 = (bj == 0) ? 2 : 2 * bj + 4;
-  c1 = 2 * bj + 5;
-}
-
-// ---------------------------------------------------------------------------------
-// force laws
-// ---------------------------------------------------------------------------------
-// particles.cpp:584-595 F12 for a pair already known to be inside the cutoff
-// (r2 < r2c <=> the clamped coefficient is > 0, see engine.cu find_r2c()).
-__device__ __forceinline__ void pair_force(const Phys& ph, float dx, float dy, float r2, float& fx, float& fy) {
-  const float r2t = (ph.thr < r2) ? r2 : ph.thr;  // std::max(threshold, r2)
-  const float inv = rcp_exact(r2t);
-  const float d2 = fmul(inv, ph.RR);
-  const float d6 = fmul(fmul(d2, d2), d2);
-  const float d12 = fmul(d6, d6);
-  const float k = fmul(fsub(d12, d6), inv);  // sigma = 1
-  fx = fmul(dx, k);
-  fy = fmul(dy, k);
-}
-// particles.cpp:572-582 / :738-749: no threshold, clamp by std::max<Scal>(0., .)
-__device__ __forceinline__ void lj_noclamp(float RR, float px, float py, float qx, float qy, float& fx, float& fy) {
-  const float dx = fsub(px, qx), dy = fsub(py, qy);
-  const float r2 = dot2(dx, dy, dx, dy);
-  const float inv = rcp_exact(r2);
-  const float d2 = fmul(inv, RR);
-  const float d6 = fmul(fmul(d2, d2), d2);
-  const float d12 = fmul(d6, d6);
-  const float k = max0(fmul(fsub(d12, d6), inv));
-  fx = fmul(dx, k);
-  fy = fmul(dy, k);
-}
-// particles.cpp:727-736 F12_bond
-__device__ __forceinline__ void bond_force(const Phys& ph, float px, float py, float qx, float qy, float& fx, float& fy) {
-  const float dx = fsub(px, qx), dy = fsub(py, qy);
-  const float r = len2(dx, dy);
-  // k = max(1. - r/R, 1. - 5) in double, rounded to float.  1 - x is exact in
-  // double for float x >= 2^-29 and rounds to 1.0f either way below that, so
-  // the float subtraction gives the same float; -4 is exact.
-  const float q = div_by_bondR(r, ph.bondR, ph.bond_y);
-  float k = fsub(1.0f, q);
-  k = (k < -4.0f) ? -4.0f : k;  // std::max(a, b) = (a < b) ? b : a
-  const float s = fmul(ph.sigma_bond, k);
-  fx = fmul(dx, s);
-  fy = fmul(dy, s);
-}
-
-// particles.h:37-46 line::GetNearest
-__device__ __forceinline__ void seg_nearest(float ax, float ay, float bx, float by, float px, float py, float& qx, float& qy) {
-  const float abx = fsub(bx, ax), aby = fsub(by, ay);
-  const float apx = fsub(px, ax), apy = fsub(py, ay);
-  const float lambda = fdiv(dot2(abx, aby, apx, apy), dot2(abx, aby, abx, aby));
-  if (lambda > 0.0f && lambda < 1.0f) {
-    qx = fadd(ax, fmul(abx, lambda));
-    qy = fadd(ay, fmul(aby, lambda));
-  } else {
-    const float da = len2(fsub(ax, px), fsub(ay, py));  // p.dist(A) = (A - p).length()
-    const float db = len2(fsub(bx, px), fsub(by, py));
-    if (da < db) { qx = ax; qy = ay; } else { qx = bx; qy = by; }
-  }
-}
-
-// lambda / offset of point p in the frame of a portal (e.g. particles.cpp:340-341)
-__device__ __forceinline__ void portal_coords(const PortalSide& s, float px, float py, float& lambda, float& offset) {
-  const float dx = fsub(px, s.ax), dy = fsub(py, s.ay);
-  lambda = fdiv(dot2(s.rx, s.ry, dx, dy), s.rr);
-  offset = dot2(dx, dy, s.nx, s.ny);
-}
-// a + r*lambda + n*(offset + 2.*sign*thickness)   (particles.cpp:369-371, 810-812)
-__device__ __forceinline__ void portal_image(const Phys& ph, const PortalSide& s, float lambda_q, float offset_q, float sign, float& x, float& y) {
-  const float shifted = __double2float_rn(__dadd_rn((double)offset_q, __dmul_rn(__dmul_rn(2.0, (double)sign), (double)ph.portal_thickness)));
-  x = fadd(fadd(s.ax, fmul(s.rx, lambda_q)), fmul(s.nx, shifted));
-  y = fadd(fadd(s.ay, fmul(s.ry, lambda_q)), fmul(s.ny, shifted));
-}
-
-__device__ __forceinline__ bool in_sorted(const int* __restrict__ list, int n, int v) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (list[mid] < v) lo = mid + 1; else hi = mid;
-  }
-  return lo < n && list[lo] == v;
-}
-
-// ---------------------------------------------------------------------------------
-// all forces on one particle (particles.cpp:839-910 calc_forces, :761-826 RHS_bonds,
-// :318-381 ApplyPortalsForces), summed in the reference's order of force kinds
-// ---------------------------------------------------------------------------------
-// Position of a bond partner given its entry in the id -> slot map: a local slot (>= 0), a ghost
-// reference -2 - (side * ghost_cap + index) into the neighbour strip's boundary rows, or -1
-// (partner left the grid: the bond is erased by CheckBonds, particles.cpp:205-215).
-template <bool STRIPS>
-__device__ __forceinline__ float2 bond_partner_pos(const StageArgs& a, const float2* __restrict__ X, int sb) {
-  if (sb >= 0) return __ldg(X + sb);
-  if (STRIPS && sb <= -2) {
-    const int code = -2 - sb;
-    const int side = code >= a.ghost_cap;
-    return __ldg(a.gpos[side] + (code - side * a.ghost_cap));
-  }
-  return make_float2(0.f, 0.f);
-}
-
-constexpr int kHitQueue = 6;     // pending in-range pairs per thread (shared memory)
-constexpr int kBondPlan = 6;     // bond partners per particle resolved up front / handed from stage 1 to stage 2
-struct HitQueue {
-  float dx[kHitQueue][kThreads];
-  float dy[kHitQueue][kThreads];
-};
-
-// One queued pair: the exact r^2 (reference rounding) decides, the prefilter only proposed it.
-__device__ __forceinline__ void eval_hit(const Phys& ph, float dx, float dy, float& fx, float& fy) {
-  const float r2 = dot2(dx, dy, dx, dy);
-  if (r2 < ph.r2c) {
-    float px, py;
-    pair_force(ph, dx, dy, r2, px, py);
-    fx = fadd(fx, px);
-    fy = fadd(fy, py);
-  }
-}
-
-// FEAT selects what the scene uses, so that unused force kinds cost neither instructions nor
-// registers: 1 = bonds, 2 = portals, 4 = mouse point force / pick, 8 = strip decomposition
-// (ghost rows, ghost bond partners); launch_stage picks the variant.
-constexpr int kFeatBonds = 1, kFeatPortals = 2, kFeatExtras = 4, kFeatStrips = 8;
 template <int STAGE, int FEAT>
 __device__ __forceinline__ float2 particle_force(
     const StageArgs& a, const float2* __restrict__ X, HitQueue& hq, int slot, int pid, float2 x, float2 v,
@@ -549,81 +331,6 @@ __device__ __forceinline__ float2 particle_force(
   return make_float2(fx, fy);
 }
 
-// particles.cpp:117-120: if (|v| > limit) v *= limit / |v|
-// fl(sqrt(v2)) > limit  <=>  v2 > v2c (sqrt is monotone; v2c found by bisection on the host), so
-// the square root is only taken when the clamp fires.
-__device__ __forceinline__ void clamp_velocity(const Phys& ph, float& vx, float& vy) {
-  const float v2 = dot2(vx, vy, vx, vy);
-  if (v2 > ph.v2c) {
-    const float l = __fsqrt_rn(v2);
-    const float s = fdiv(ph.vlimit, l);
-    vx = fmul(vx, s);
-    vy = fmul(vy, s);
-  }
-}
-
-// DetectPortals + ApplyPortals (particles.cpp:288-316, 382-409) for one particle whose
-// reference block is `blk`, then the new sub-cell key and the histogram update
-// (the device half of blocks::SortParticles, blocks.h:215-244).
-template <class A>
-__device__ __forceinline__ void teleport(const A& a, int blk, float2& x, float2& v) {
-  bool flagged = false;
-  for (int s = 0; s < a.n_sides; ++s) {
-    const int lb = a.pblk_ptr[s], le = a.pblk_ptr[s + 1];
-    if (!in_sorted(a.pblk + lb, le - lb, blk)) continue;
-    float lambda, offset;
-    portal_coords(a.sides[s], x.x, x.y, lambda, offset);
-    if (lambda > 0.0f && lambda < 1.0f && fabsf(offset) <= a.ph.portal_thickness) flagged = true;
-  }
-  if (!flagged) return;
-  for (int s = 0; s < a.n_sides; ++s) {  // first (pair, side) whose block list holds the particle
-    const int lb = a.pblk_ptr[s], le = a.pblk_ptr[s + 1];
-    if (!in_sorted(a.pblk + lb, le - lb, blk)) continue;
-    const PortalSide src = a.sides[s];
-    const PortalSide dst = a.sides[s ^ 1];
-    // MoveToPortal (particles.cpp:264-286)
-    float lambda_pos, offset_pos;
-    portal_coords(src, x.x, x.y, lambda_pos, offset_pos);
-    // offset_pos there is src_n.dot(position - src_a): same products, same sum
-    const float lambda_vel = fdiv(dot2(src.rx, src.ry, v.x, v.y), src.rr);
-    const float offset_vel = dot2(src.nx, src.ny, v.x, v.y);
-    const float sign = (offset_pos > 0.0f) ? 1.0f : -1.0f;
-    const float shifted = __double2float_rn(
-        __dsub_rn((double)offset_pos, __dmul_rn(__dmul_rn((double)sign, 2.0), (double)a.ph.portal_thickness)));
-    x.x = fadd(fadd(dst.ax, fmul(dst.rx, lambda_pos)), fmul(dst.nx, shifted));
-    x.y = fadd(fadd(dst.ay, fmul(dst.ry, lambda_pos)), fmul(dst.ny, shifted));
-    const float vx = fadd(fmul(dst.rx, lambda_vel), fmul(dst.nx, offset_vel));
-    const float vy = fadd(fmul(dst.ry, lambda_vel), fmul(dst.ny, offset_vel));
-    v.x = vx;
-    v.y = vy;
-    return;
-  }
-}
-
-// New sub-cell of a particle after the update + histogram (the device half of
-// blocks::SortParticles).  A particle whose new sub-row belongs to another strip is put into
-// that strip's outbox (with its old slot, which fixes its place in the receiver's stable order)
-// and leaves this strip through the trash bin.
-__device__ __forceinline__ void key_and_count(const GridDev& g, const DistDev& d, float2 x, float2 v,
-                                              const int* __restrict__ id, int slot, unsigned* newcell, int* cnt) {
-  const Cell c = cell_of_fast(g, x);
-  bool migrant;
-  const unsigned pc = pack_cell(g, c, migrant);
-  if (migrant && d.out_base) {
-    int dest = 0;
-    while (dest + 1 < d.world && c.Si >= d.row_begin[dest + 1]) ++dest;
-    char* blk = d.out_base + dest * d.out_stride;
-    const int k = atomicAdd(reinterpret_cast<int*>(blk), 1);
-    if (k < d.out_cap) {
-      reinterpret_cast<float2*>(blk + mig_off_pos())[k] = x;
-      reinterpret_cast<float2*>(blk + mig_off_vel(d.out_cap))[k] = v;
-      reinterpret_cast<int*>(blk + mig_off_id(d.out_cap))[k] = id[slot];
-      reinterpret_cast<int*>(blk + mig_off_tag(d.out_cap))[k] = slot;
-    }
-  }
-  newcell[slot] = pc;
-  atomicAdd(cnt + key_of_packed(pc, g.SJ, g.ncell), 1);  // result unused -> RED.ADD
-}
 
 template <int STAGE, int FEAT>
 __global__ void __launch_bounds__(kThreads, (FEAT & kFeatBonds) ? PTOY_STAGE_MINB_BONDS : PTOY_STAGE_MINB) stage_kernel(const __grid_constant__ StageArgs a) {
@@ -637,8 +344,8 @@ __global__ void __launch_bounds__(kThreads, (FEAT & kFeatBonds) ? PTOY_STAGE_MIN
   __shared__ HitQueue hq;
   // the sub-cell this particle was binned into (stored by the reorder), and its approximate
   // fractional position inside it (only compared against the search margin)
-  const unsigned pc = a.cell[i];
-  const int Si = (int)(pc >> 16), Sj = (int)(pc & 0xffffu);
+  const int ck = a.cell[i];
+  const int Si = ck / a.g.SJ, Sj = ck - Si * a.g.SJ;
   const float ui = fsub(x0.x, a.g.Ax) * a.g.inv_hsx - (float)(Si + a.g.row0 - 4);
   const float uj = fsub(x0.y, a.g.Ay) * a.g.inv_hsy - (float)(Sj - 4);
   int blk = 0;
@@ -704,15 +411,24 @@ __global__ void __launch_bounds__(kThreads) tail_kernel(const __grid_constant__ 
 // ---------------------------------------------------------------------------------
 // single-pass exclusive scan (decoupled look-back), 1024 ints per tile
 // ---------------------------------------------------------------------------------
-constexpr int kScanItems = 16;  // consecutive ints per thread (4 x int4)
-constexpr int kScanTile = kThreads * kScanItems;
+#ifndef PTOY_SCAN_THREADS
+#define PTOY_SCAN_THREADS 512
+#endif
+#ifndef PTOY_SCAN_ITEMS
+#define PTOY_SCAN_ITEMS 32
+#endif
+// Large tiles keep the look-back chain short (tiles / 32 rounds of one L2 round trip each): at
+// 16M particles the histogram has 14M entries = 870 tiles of 16384.
+constexpr int kScanThreads = PTOY_SCAN_THREADS;
+constexpr int kScanItems = PTOY_SCAN_ITEMS;  // consecutive ints per thread (int4 loads)
+constexpr int kScanTile = kScanThreads * kScanItems;
 int scan_tile_items() { return kScanTile; }
 
-__global__ void __launch_bounds__(kThreads) scan_kernel(
-    const int* __restrict__ cnt, int* __restrict__ start, int n_items, int ncell,
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(
+    int* __restrict__ cnt, int* __restrict__ start, int n_items, int ncell,
     unsigned long long* tile_state, int* ticket, unsigned epoch, Counters* ctr) {
   __shared__ int s_tile;
-  __shared__ int s_warp[kThreads / 32];
+  __shared__ int s_warp[kScanThreads / 32];
   __shared__ int s_prefix;
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
   __syncthreads();
@@ -722,7 +438,10 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(
 #pragma unroll
   for (int k = 0; k < kScanItems; k += 4) {
     int4 q = make_int4(0, 0, 0, 0);
-    if (base + k < n_items) q = *reinterpret_cast<const int4*>(cnt + base + k);  // n_items % 4 == 0
+    if (base + k < n_items) {  // n_items % 4 == 0; the histogram is handed back all-zero
+      q = *reinterpret_cast<const int4*>(cnt + base + k);
+      *reinterpret_cast<int4*>(cnt + base + k) = make_int4(0, 0, 0, 0);
+    }
     v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
   }
   int tsum = 0;
@@ -738,22 +457,24 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    int w = (lane < kThreads / 32) ? s_warp[lane] : 0;
+    int w = (lane < kScanThreads / 32) ? s_warp[lane] : 0;
 #pragma unroll
-    for (int o = 1; o < kThreads / 32; o <<= 1) {
+    for (int o = 1; o < kScanThreads / 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, w, o);
       if (lane >= o) w += t;
     }
-    if (lane < kThreads / 32) s_warp[lane] = w;  // inclusive over warps
+    if (lane < kScanThreads / 32) s_warp[lane] = w;  // inclusive over warps
   }
   __syncthreads();
-  const int block_total = s_warp[kThreads / 32 - 1];
+  const int block_total = s_warp[kScanThreads / 32 - 1];
   const int excl_in_block = incl - tsum + (warp ? s_warp[warp - 1] : 0);
 
   // publish aggregate / look back.  state = (epoch*4 + flag) << 32 | value; flag 1 = this tile's
   // total, flag 2 = inclusive prefix.  Warp 0 looks at 32 predecessors per round: lane l reads
   // tile t - l, the nearest one that already holds an inclusive prefix ends the walk.
-  const unsigned long long tag = (unsigned long long)epoch << 2;
+  // (30 bits of epoch: the tag and the flag share the upper word; every tile rewrites its state
+  // each scan, so a value from 2^30 scans ago cannot be met)
+  const unsigned long long tag = (unsigned long long)(epoch & 0x3fffffffu) << 2;
   if (warp == 0) {
     volatile unsigned long long* st = tile_state;
     int prefix = 0;
@@ -803,71 +524,102 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(
 }
 
 // ---------------------------------------------------------------------------------
-// counting-sort fill + deterministic gather
+// reorder: one scatter pass + a fix-up of the few cells whose order it could not decide
+// (the device half of blocks::SortParticles, blocks.h:215-244)
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) fill_kernel(const __grid_constant__ ReorderArgs a) {
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  if (i >= a.ctr->n_cur + a.ctr->n_arrived) return;
-  const int key = key_of_packed(a.newcell[i], a.SJ, a.ncell);
-  // counting down leaves the histogram all-zero again for the next iteration; the first atomic
-  // served takes the first slot of the run, so that the usual service order (ascending old
-  // slot) already is the stable order gather_kernel wants
-  const int left = atomicSub(a.cnt + key, 1);
-  a.order[a.start[key + 1] - left] = i;
+// The reorder is the STABLE sort by new sub-cell key: members of a cell keep the order of their
+// old slots (arrivals from other strips: of their (source rank, old slot) tags), so the result
+// does not depend on the order in which atomics are served and N strips equal one GPU bit for
+// bit.  A thread per OLD slot moves its particle straight to its new slot, both sides nearly
+// coalesced because few particles change cell per step:
+//   * fast path (almost every particle): all m members of the new cell form one run of
+//     consecutive old slots around this one (checked in shared memory against the cell's
+//     population m = start[key + 1] - start[key]); its place is the run offset;
+//   * otherwise (somebody entered the cell from another sub-row, from another strip, through a
+//     portal, or the cell holds more than kApron particles) every member takes a slot of the
+//     cell from an atomic counter, leaves its old slot as a tag, and the first one files the
+//     cell for fixup_kernel, which re-places the members by their tags.
+constexpr int kApron = 8;
+
+__device__ __forceinline__ unsigned long long reorder_vkey(const ReorderArgs& a, int i, int n_loc) {
+  return i < n_loc ? ((unsigned long long)a.rank << 32) | (unsigned)i : a.arr_vkey[i - n_loc];
 }
 
-// New slot k receives the particle with the (k - start[c])-th smallest OLD slot among
-// the particles of its sub-cell c: the result is the stable sort by key, independent of
-// the order in which fill_kernel's atomics were served.  The payload of the particle
-// fill_kernel put at k is loaded before that is checked (it is the right one unless the
-// atomics of a shared cell were served out of order).
-__global__ void __launch_bounds__(kThreads, 8) gather_kernel(const __grid_constant__ ReorderArgs a) {
-  const int k = blockIdx.x * kThreads + threadIdx.x;
-  if (k >= a.ctr->n_total) return;
-  const int src0 = a.order[k];
-  if (k >= a.ctr->n_next) {  // left the grid: removed (blocks.h:230-232)
-    if (a.slot_of_id) a.slot_of_id[a.id_in[src0]] = -1;
+__global__ void __launch_bounds__(kThreads) scatter_kernel(const __grid_constant__ ReorderArgs a) {
+  __shared__ int s_key[kThreads + 2 * kApron];
+  const int n_loc = a.ctr->n_cur, n_in = n_loc + a.ctr->n_arrived;
+  const int i0 = blockIdx.x * kThreads;
+  if (i0 >= n_in) return;
+  for (int idx = threadIdx.x; idx < kThreads + 2 * kApron; idx += kThreads) {
+    const int j = i0 - kApron + idx;
+    s_key[idx] = (j >= 0 && j < n_in) ? a.newcell[j] : -1;
+  }
+  __syncthreads();
+  const int i = i0 + threadIdx.x;
+  if (i >= n_in) return;
+  const int* sk = s_key + kApron + threadIdx.x;
+  const int key = sk[0];
+  const float2 p = a.pos_in[i], v = a.vel_in[i];
+  const int pid = a.id_in[i];
+  if (key == a.ncell) {  // left the grid (blocks.h:230-232) or moved to another strip
+    if (a.slot_of_id) a.slot_of_id[pid] = kSlotNone;
     return;
   }
-  const unsigned pc = a.newcell[src0];
-  float2 p = a.pos_in[src0];
-  float2 v = a.vel_in[src0];
-  int pid = a.id_in[src0];
-  const int c = key_of_packed(pc, a.SJ, a.ncell);
-  const int beg = a.start[c], end = a.start[c + 1];
-  if (end - beg > 1) {
-    const int want = k - beg;
-    const int n_loc = a.ctr->n_cur;
-    auto vkey = [&](int i) -> unsigned long long {
-      return i < n_loc ? ((unsigned long long)a.rank << 32) | (unsigned)i : a.arr_vkey[i - n_loc];
-    };
-    auto rank_of = [&](int cand) -> int {
-      const unsigned long long ck = vkey(cand);
-      int smaller = 0;
-      for (int e2 = beg; e2 < end; ++e2) smaller += (vkey(a.order[e2]) < ck);
-      return smaller;
-    };
-    if (rank_of(src0) != want) {
-      for (int e = beg; e < end; ++e) {
-        const int cand = a.order[e];
-        if (cand != src0 && rank_of(cand) == want) {
-          p = a.pos_in[cand]; v = a.vel_in[cand]; pid = a.id_in[cand];
-          break;
-        }
-      }
-    }
+  const int beg = a.start[key], m = a.start[key + 1] - beg;
+  int dest = -1;
+  if (m <= kApron) {
+    int L = 0, R = 0;
+    while (L < kApron && sk[-1 - L] == key) ++L;
+    while (R < kApron && sk[1 + R] == key) ++R;
+    if (L + R + 1 == m && i + R < n_loc) dest = beg + L;
   }
-  a.pos_out[k] = p;
-  a.vel_out[k] = v;
-  a.id_out[k] = pid;
-  a.cell_out[k] = pc;
-  if (a.slot_of_id) a.slot_of_id[pid] = k;
+  if (dest < 0) {
+    const int r = atomicAdd(a.cnt + key, 1);
+    dest = beg + r;
+    a.tag[dest] = i;
+    if (r == 0) a.fixlist[atomicAdd(a.n_fix, 1)] = key;
+  }
+  a.pos_out[dest] = p;
+  a.vel_out[dest] = v;
+  a.id_out[dest] = pid;
+  a.cell_out[dest] = key;
+  if (a.slot_of_id) a.slot_of_id[pid] = dest;
+}
+
+// One warp per filed cell: member e (placed by the atomic counter) belongs at the rank of its tag
+// among the cell's tags; the payload is re-read from the old arrays, which are still intact.
+__global__ void __launch_bounds__(kThreads) fixup_kernel(const __grid_constant__ ReorderArgs a) {
+  const int nfix = *a.n_fix;
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * (kThreads / 32);
+  const int n_loc = a.ctr->n_cur;
+  for (int f = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); f < nfix; f += warps) {
+    const int key = a.fixlist[f];
+    const int beg = a.start[key], end = a.start[key + 1];
+    for (int e = beg + lane; e < end; e += 32) {
+      const int src = a.tag[e];
+      const unsigned long long vk = reorder_vkey(a, src, n_loc);
+      int rank = 0;
+      for (int e2 = beg; e2 < end; ++e2) rank += reorder_vkey(a, a.tag[e2], n_loc) < vk;
+      const int d = beg + rank;
+      const int pid = a.id_in[src];
+      a.pos_out[d] = a.pos_in[src];
+      a.vel_out[d] = a.vel_in[src];
+      a.id_out[d] = pid;
+      a.cell_out[d] = key;
+      if (a.slot_of_id) a.slot_of_id[pid] = d;
+    }
+    __syncwarp();
+    if (lane == 0) a.cnt[key] = 0;   // the histogram goes back all-zero
+  }
 }
 
 __global__ void finalize_kernel(Counters* ctr, int* ticket) {
   ctr->removed_total += ctr->n_total - ctr->n_next;
   ctr->n_cur = ctr->n_next;
   ctr->n_arrived = 0;
+  ctr->n_fix = 0;
+  ctr->dmax = 0u;
   *ticket = 0;
 }
 
@@ -899,9 +651,9 @@ __global__ void __launch_bounds__(kThreads) arrivals_kernel(const __grid_constan
   a.arr_vkey[off + k] = ((unsigned long long)src << 32) |
                         (unsigned)reinterpret_cast<const int*>(blk + mig_off_tag(a.in_cap))[k];
   bool migrant;
-  const unsigned pc = pack_cell(a.g, cell_of_fast(a.g, x), migrant);  // the sender routed it here
-  a.newcell[dst] = pc;
-  atomicAdd(a.cnt + key_of_packed(pc, a.g.SJ, a.g.ncell), 1);
+  const int key = cell_key(a.g, cell_of_fast(a.g, x), migrant);  // the sender routed it here
+  a.newcell[dst] = key;
+  atomicAdd(a.cnt + key, 1);
 }
 
 // Copy the two boundary sub-rows on each side into staging buffers (positions; optionally the
@@ -985,20 +737,28 @@ static void launch_stage_feat(int stage, const StageArgs& a, int n_bound, cudaSt
   if (stage == 1) stage_kernel<1, FEAT><<<grid_for(n_bound), kThreads, 0, s>>>(a);
   else stage_kernel<2, FEAT><<<grid_for(n_bound), kThreads, 0, s>>>(a);
 }
+// tile-staged kernels, one translation unit per (bonds, portals) combination (stage_tile.cu)
+void launch_stage_tile_g0(int stage, bool extras, const StageArgs& a, int n_bound, cudaStream_t s);
+void launch_stage_tile_g1(int stage, bool extras, const StageArgs& a, int n_bound, cudaStream_t s);
+void launch_stage_tile_g2(int stage, bool extras, const StageArgs& a, int n_bound, cudaStream_t s);
+void launch_stage_tile_g3(int stage, bool extras, const StageArgs& a, int n_bound, cudaStream_t s);
+
 void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound <= 0) return;
   const int feat = (a.has_bonds ? kFeatBonds : 0) | (a.n_sides > 0 ? kFeatPortals : 0) |
                    ((a.ph.force_enabled || a.ph.pick_enabled) ? kFeatExtras : 0) |
                    (a.dist.world > 1 ? kFeatStrips : 0);
+  if (!(feat & kFeatStrips)) {
+    const bool extras = (feat & kFeatExtras) != 0;
+    switch (feat & 3) {
+      case 0: launch_stage_tile_g0(stage, extras, a, n_bound, s); break;
+      case 1: launch_stage_tile_g1(stage, extras, a, n_bound, s); break;
+      case 2: launch_stage_tile_g2(stage, extras, a, n_bound, s); break;
+      default: launch_stage_tile_g3(stage, extras, a, n_bound, s); break;
+    }
+    return;
+  }
   switch (feat) {
-    case 0: launch_stage_feat<0>(stage, a, n_bound, s); break;
-    case 1: launch_stage_feat<1>(stage, a, n_bound, s); break;
-    case 2: launch_stage_feat<2>(stage, a, n_bound, s); break;
-    case 3: launch_stage_feat<3>(stage, a, n_bound, s); break;
-    case 4: launch_stage_feat<4>(stage, a, n_bound, s); break;
-    case 5: launch_stage_feat<5>(stage, a, n_bound, s); break;
-    case 6: launch_stage_feat<6>(stage, a, n_bound, s); break;
-    case 7: launch_stage_feat<7>(stage, a, n_bound, s); break;
     case 8: launch_stage_feat<8>(stage, a, n_bound, s); break;
     case 9: launch_stage_feat<9>(stage, a, n_bound, s); break;
     case 10: launch_stage_feat<10>(stage, a, n_bound, s); break;
@@ -1013,18 +773,20 @@ void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound - a.first <= 0) return;
   tail_kernel<<<grid_for(n_bound - a.first), kThreads, 0, s>>>(a);
 }
-void launch_scan(const int* cnt, int* start, int n_items, int ncell, unsigned long long* tile_state,
+void launch_scan(int* cnt, int* start, int n_items, int ncell, unsigned long long* tile_state,
                  int* ticket, unsigned epoch, Counters* ctr, cudaStream_t s) {
   const int tiles = (n_items + kScanTile - 1) / kScanTile;
-  scan_kernel<<<tiles, kThreads, 0, s>>>(cnt, start, n_items, ncell, tile_state, ticket, epoch, ctr);
+  scan_kernel<<<tiles, kScanThreads, 0, s>>>(cnt, start, n_items, ncell, tile_state, ticket, epoch, ctr);
 }
-void launch_fill(const ReorderArgs& a, int n_bound, cudaStream_t s) {
+void launch_scatter(const ReorderArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound <= 0) return;
-  fill_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(a);
+  scatter_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(a);
 }
-void launch_gather(const ReorderArgs& a, int n_bound, cudaStream_t s) {
+void launch_fixup(const ReorderArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound <= 0) return;
-  gather_kernel<<<grid_for(n_bound), kThreads, 0, s>>>(a);
+  // a grid-stride loop over the filed cells (usually a handful): a fixed, small grid
+  const unsigned grid = (unsigned)std::min<size_t>(grid_for(n_bound), 148 * 4);
+  fixup_kernel<<<grid, kThreads, 0, s>>>(a);
 }
 __global__ void __launch_bounds__(kThreads) ghost_map_kernel(const __grid_constant__ GhostMapArgs a) {
   const int side = blockIdx.y;

@@ -91,7 +91,7 @@ SIGNATURES = {
 # entry points that do not take a handle first
 FREE_FUNCTIONS = ["ptoy_last_error", "ptoy_abi_version", "ptoy_create", "ptoy_destroy",
                   "ptoy_nccl_unique_id", "ptoy_group_create", "ptoy_group_step_n", "ptoy_group_destroy"]
-KERNEL_KINDS = ["stage1", "stage2", "scan", "fill", "gather", "other"]
+KERNEL_KINDS = ["stage1", "stage2", "scan", "scatter", "fixup", "other"]
 
 TOOLS = {"bonds": 0, "pick": 1, "freeze": 2, "portal": 3}
 PHASES = {"start": 0, "move": 1, "stop": 2}

@@ -40,8 +40,14 @@ namespace ptoy {
 
 constexpr int kTile = PTOY_TILE;              // particles per tile = consumer threads per CTA
 constexpr int kTileThreads = kTile + 32;      // + one producer warp
-constexpr int kWinCap = kTile + 80;           // staged particles per row window
-constexpr int kKeyCap = kTile + 128;          // staged start[] entries per row window
+#ifndef PTOY_TILE_WINCAP
+#define PTOY_TILE_WINCAP (PTOY_TILE + 80)
+#endif
+#ifndef PTOY_TILE_KEYCAP
+#define PTOY_TILE_KEYCAP (PTOY_TILE + 128)
+#endif
+constexpr int kWinCap = PTOY_TILE_WINCAP;     // staged particles per row window
+constexpr int kKeyCap = PTOY_TILE_KEYCAP;     // staged start[] entries per row window
 
 // One pipeline slot: everything a tile's consumer threads read, filled by the bulk-copy engine.
 template <int STAGE>
@@ -53,12 +59,13 @@ struct TileBuf {
   alignas(16) int id[kTile];            // ... ids (when the scene needs them)
   alignas(16) float2 pos0[STAGE == 2 ? kTile : 2];   // stage 2: x0, v0
   alignas(16) float2 vel0[STAGE == 2 ? kTile : 2];
-  // descriptor, written by the producer before it arms the barrier
-  int k0, k1;       // the tile's particles
-  int staged;       // row windows are in shared memory (else: the search reads global memory)
-  int cA;           // sort key of the tile's first particle
-  int soff[3];      // start[w][soff[w] + (key - cA) + dc] = start[key + (w - 1) * SJ + dc]
-  int poff[3];      // pos[w][slot + poff[w]] = position of `slot`
+  // descriptor, written by the producer (three 16-byte stores) before it arms the barrier
+  alignas(16) int k0;   // the tile's particles [k0, k1)
+  int k1;
+  int staged;           // row windows are in shared memory (else: the search reads global memory)
+  int cA;               // sort key of the tile's first particle
+  alignas(16) int soff[4];   // start[w][soff[w] + (key - cA) + dc] = start[key + (w - 1) * SJ + dc]
+  alignas(16) int poff[4];   // pos[w][slot + poff[w]] = position of `slot`
 };
 
 template <int STAGE>
@@ -103,11 +110,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // body, the outcome goes into a bit mask), phase 2 walks the set bits in candidate order and
 // evaluates those pairs with the reference's exact arithmetic (particles.cpp:584-595; the exact
 // r^2 decides).  Contributions are summed in slot order, like the plain loop would.
-// SELF: the window is the particle's own row and contains the particle itself (slot `self`),
-// which the reference skips by address (particles.cpp:601).
-template <bool SELF>
+// `self`: slot of the particle itself when the window is its own row (the reference skips it by
+// address, particles.cpp:601), a slot outside [b, e) otherwise.
+constexpr int kNoSelf = -0x40000000;
+
 __device__ __forceinline__ void row_scan(const float2* __restrict__ P, int b, int e, int self, float2 x,
-                                         float r2c_hi, const Phys& ph, float& fx, float& fy) {
+                                         const Phys& ph, float& fx, float& fy) {
+  const float thr = ph.r2c_hi;
   while (b < e) {
     const int m = min(e - b, 32);
     unsigned mask = 0u, bit = 1u;
@@ -118,16 +127,17 @@ __device__ __forceinline__ void row_scan(const float2* __restrict__ P, int b, in
       const float dx0 = fsub(x.x, p0.x), dy0 = fsub(x.y, p0.y);
       const float dx1 = fsub(x.x, p1.x), dy1 = fsub(x.y, p1.y);
       const float r0 = __fmaf_rn(dx0, dx0, dy0 * dy0), r1 = __fmaf_rn(dx1, dx1, dy1 * dy1);
-      if (r0 < r2c_hi) mask |= bit;
-      if (r1 < r2c_hi) mask |= bit << 1;
+      if (r0 < thr) mask |= bit;
+      if (r1 < thr) mask |= bit << 1;
       bit <<= 2;
     }
     if (k < m) {
       const float2 p0 = P[b + k];
       const float dx0 = fsub(x.x, p0.x), dy0 = fsub(x.y, p0.y);
-      if (__fmaf_rn(dx0, dx0, dy0 * dy0) < r2c_hi) mask |= bit;
+      if (__fmaf_rn(dx0, dx0, dy0 * dy0) < thr) mask |= bit;
     }
-    if (SELF) { const unsigned d = (unsigned)(self - b); if (d < 32u) mask &= ~(1u << d); }
+    const unsigned d = (unsigned)(self - b);
+    if (d < 32u) mask &= ~(1u << d);
     while (mask) {
       const int h = __ffs(mask) - 1;
       mask &= mask - 1u;
@@ -142,6 +152,27 @@ __device__ __forceinline__ void row_scan(const float2* __restrict__ P, int b, in
       }
     }
     b += m;
+  }
+}
+
+// The pair search of one particle over its 3 (5) row windows.  s0..s2 point at the start[] entry
+// of the particle's own column in row window -1, 0, +1 (s[dc] = first slot of column dc),
+// P0..P2[slot] is the position of `slot` in that window; both in shared memory for a staged
+// tile, in global memory otherwise.  Rows +-2 (a particle near a cell edge in x) come from
+// global memory.
+__device__ __forceinline__ void pair_search(const int* __restrict__ s0, const int* __restrict__ s1, const int* __restrict__ s2,
+                                            const float2* __restrict__ P0, const float2* __restrict__ P1,
+                                            const float2* __restrict__ P2, const float2* __restrict__ X,
+                                            const int* __restrict__ gs, int SJ, bool near_i, bool near_j, int self,
+                                            float2 x, const Phys& ph, float& fx, float& fy) {
+  const int dlo = -1 - (int)near_j, dhi = 2 + (int)near_j;   // columns [dlo, dhi)
+  const int b0 = s0[dlo], e0 = s0[dhi], b1 = s1[dlo], e1 = s1[dhi], b2 = s2[dlo], e2 = s2[dhi];
+  row_scan(P0, b0, e0, kNoSelf, x, ph, fx, fy);
+  row_scan(P1, b1, e1, self, x, ph, fx, fy);
+  row_scan(P2, b2, e2, kNoSelf, x, ph, fx, fy);
+  if (near_i) {   // the rare fourth and fifth row
+    row_scan(X, __ldg(gs - 2 * SJ + dlo), __ldg(gs - 2 * SJ + dhi), kNoSelf, x, ph, fx, fy);
+    row_scan(X, __ldg(gs + 2 * SJ + dlo), __ldg(gs + 2 * SJ + dhi), kNoSelf, x, ph, fx, fy);
   }
 }
 
@@ -327,12 +358,14 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
 
   if (t >= kTile) {
     // ================= producer warp: describe tile, start its bulk copies ====================
-    // Software-pipelined over the tile sequence so that the only latency left between "slot
-    // free" and "copies issued" is the copies' own: while tile T is being described from values
-    // already in registers, the start[] bounds of tile T+1 and the first / last sort key of tile
-    // T+2 are on their way.
+    // One copy per lane: lanes 0-2 the start[] slices of row windows -1, 0, +1, lanes 3-5 their
+    // position windows, 6 the tile's velocities, 7 sort keys, 8 ids, 9-11 (stage 2) x0, v0 and the
+    // neighbour lists.  Everything about tile T is worked out BEFORE waiting for its slot, so
+    // that what follows the wait is: descriptor store, arm the barrier, one copy per lane.  The
+    // loads it needs are software-pipelined over the tile sequence: while T is described from
+    // registers, the start[] bounds of T+1 and the first / last sort key of T+2 are on their way.
     const int lane = t - kTile;
-    const int w = lane < 3 ? lane : 0;
+    const int w = lane % 3;
     const int G = gridDim.x;
     auto load_keys = [&](int tile, int& cA, int& cB) {
       cA = 0; cB = 0;
@@ -346,7 +379,7 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
     auto load_bounds = [&](int tile, int cA, int cB, int& sb, int& se) {
       sb = 0; se = 0;
       const int kb = cA + (w - 1) * SJ - 2, nkeys = cB - cA + 5;
-      if (tile * kTile < n && ((kb + nkeys + 1 - (kb & ~3) + 3) & ~3) <= kKeyCap) {
+      if (lane < 6 && tile * kTile < n && ((kb + nkeys + 1 - (kb & ~3) + 3) & ~3) <= kKeyCap) {
         sb = __ldg(a.start + kb);
         se = __ldg(a.start + kb + nkeys);
       }
@@ -361,7 +394,7 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
       load_keys(tile0 + 2 * G, cA2, cB2);
       const int b = it % NB;
       TileBuf<STAGE>& B = sm.buf[b];
-      while (!mbar_try_wait(&sm.empty[b], ((it / NB) & 1) ^ 1)) {}
+      // ---- describe the tile ---------------------------------------------------------------
       const int k0 = tile0 * kTile, k1 = min(k0 + kTile, n);
       const int nkeys = cB0 - cA0 + 5;
       const int kb = cA0 + (w - 1) * SJ - 2;
@@ -369,33 +402,36 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
       const int nk = (kb + nkeys + 1 - kb_al + 3) & ~3;   // start[] entries to stage
       const int pb = sb0 & ~1;
       const int np = ((se0 + 1) & ~1) - pb;
-      const bool ok = nk <= kKeyCap && np <= kWinCap;
-      const bool staged = __all_sync(0xffffffffu, ok || lane >= 3);
+      const bool staged = __all_sync(0xffffffffu, lane >= 6 || (nk <= kKeyCap && np <= kWinCap));
       const unsigned own_f2 = (unsigned)(((k1 - k0) + 1) & ~1) * 8u;   // float2 tiles
       const unsigned own_i = (unsigned)(((k1 - k0) + 3) & ~3) * 4u;    // int tiles
-      unsigned total = (staged && lane < 3) ? (unsigned)(nk * 4 + np * 8) : 0u;
-      total += __shfl_down_sync(0xffffffffu, total, 2);
-      total += __shfl_down_sync(0xffffffffu, total, 1);
-      total += own_f2 + own_i + (a.need_id ? own_i : 0u) + (STAGE == 2 ? 2u * own_f2 : 0u);
-      const int pb1 = __shfl_sync(0xffffffffu, pb, 1), pb2 = __shfl_sync(0xffffffffu, pb, 2);
+      const void* src = nullptr;
+      void* dst = nullptr;
+      unsigned bytes = 0u;
+      if (lane < 3) { src = a.start + kb_al; dst = &B.start[w][0]; bytes = staged ? (unsigned)nk * 4u : 0u; }
+      else if (lane < 6) { src = X + pb; dst = &B.pos[w][0]; bytes = staged ? (unsigned)np * 8u : 0u; }
+      else if (lane == 6) { src = (STAGE == 1 ? a.vel : (const float2*)a.vel_h) + k0; dst = &B.vel[0]; bytes = own_f2; }
+      else if (lane == 7) { src = a.cell + k0; dst = &B.key[0]; bytes = own_i; }
+      else if (lane == 8) { src = a.id + k0; dst = &B.id[0]; bytes = a.need_id ? own_i : 0u; }
+      else if (STAGE == 2 && lane == 9) { src = a.pos + k0; dst = &B.pos0[0]; bytes = own_f2; }
+      else if (STAGE == 2 && lane == 10) { src = a.vel + k0; dst = &B.vel0[0]; bytes = own_f2; }
+      const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
       const int ko = kb - kb_al + 2;
-      const int ko1 = __shfl_sync(0xffffffffu, ko, 1), ko2 = __shfl_sync(0xffffffffu, ko, 2);
+      const int4 d0 = make_int4(k0, k1, (int)staged, cA0);
+      const int4 d1 = make_int4(__shfl_sync(0xffffffffu, ko, 0), __shfl_sync(0xffffffffu, ko, 1),
+                                __shfl_sync(0xffffffffu, ko, 2), 0);
+      const int4 d2 = make_int4(-__shfl_sync(0xffffffffu, pb, 3), -__shfl_sync(0xffffffffu, pb, 4),
+                                -__shfl_sync(0xffffffffu, pb, 5), 0);
+      // ---- wait for the slot, publish, copy -----------------------------------------------------
+      while (!mbar_try_wait(&sm.empty[b], ((it / NB) & 1) ^ 1)) {}
       if (lane == 0) {
-        B.k0 = k0; B.k1 = k1; B.staged = staged; B.cA = cA0;
-        B.poff[0] = -pb; B.poff[1] = -pb1; B.poff[2] = -pb2;
-        B.soff[0] = ko; B.soff[1] = ko1; B.soff[2] = ko2;
+        *reinterpret_cast<int4*>(&B.k0) = d0;
+        *reinterpret_cast<int4*>(&B.soff[0]) = d1;
+        *reinterpret_cast<int4*>(&B.poff[0]) = d2;
         mbar_arrive_expect_tx(&sm.full[b], total);
       }
       __syncwarp();
-      if (staged && lane < 3) {
-        bulk_g2s(&B.start[w][0], a.start + kb_al, (unsigned)nk * 4u, &sm.full[b]);
-        if (np > 0) bulk_g2s(&B.pos[w][0], X + pb, (unsigned)np * 8u, &sm.full[b]);
-      }
-      if (lane == 3) bulk_g2s(&B.vel[0], (STAGE == 1 ? a.vel : (const float2*)a.vel_h) + k0, own_f2, &sm.full[b]);
-      if (lane == 4) bulk_g2s(&B.key[0], a.cell + k0, own_i, &sm.full[b]);
-      if (lane == 5 && a.need_id) bulk_g2s(&B.id[0], a.id + k0, own_i, &sm.full[b]);
-      if (STAGE == 2 && lane == 6) bulk_g2s(&B.pos0[0], a.pos + k0, own_f2, &sm.full[b]);
-      if (STAGE == 2 && lane == 7) bulk_g2s(&B.vel0[0], a.vel + k0, own_f2, &sm.full[b]);
+      if (bytes) bulk_g2s(dst, src, bytes, &sm.full[b]);
       tile0 += G;
       cA0 = cA1; cB0 = cB1; sb0 = sb1; se0 = se1;
       cA1 = cA2; cB1 = cB2;
@@ -410,7 +446,6 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
   float margin = a.margin;
   if (STAGE == 2 && a.dmax) margin = fminf(a.margin, a.margin_base + a.margin_scale * __uint_as_float(*a.dmax));
   const float margin_hi = 1.0f - margin;
-  const float r2c_hi = ph.r2c_hi;
   float drift_max = 0.0f;
 
   int it = 0;
@@ -479,32 +514,14 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
       }
 
       // ---- pair forces over the sub-cell neighbourhood -------------------------------------------
-      {
-        const int dlo = -1 - (int)near_j, dhi = 2 + (int)near_j;   // columns [dlo, dhi)
-        if (staged) {
-          const int cr = ck - B.cA;
-          const int* s0 = &B.start[0][B.soff[0] + cr];
-          const int* s1 = &B.start[1][B.soff[1] + cr];
-          const int* s2 = &B.start[2][B.soff[2] + cr];
-          const int b0 = s0[dlo], e0 = s0[dhi], b1 = s1[dlo], e1 = s1[dhi], b2 = s2[dlo], e2 = s2[dhi];
-          row_scan<false>(&B.pos[0][0] + B.poff[0], b0, e0, i, x, r2c_hi, ph, fx, fy);
-          row_scan<true>(&B.pos[1][0] + B.poff[1], b1, e1, i, x, r2c_hi, ph, fx, fy);
-          row_scan<false>(&B.pos[2][0] + B.poff[2], b2, e2, i, x, r2c_hi, ph, fx, fy);
-        } else {
-          const int* sp = a.start + ck - SJ;
-          const int b0 = __ldg(sp + dlo), e0 = __ldg(sp + dhi);
-          const int b1 = __ldg(sp + SJ + dlo), e1 = __ldg(sp + SJ + dhi);
-          const int b2 = __ldg(sp + 2 * SJ + dlo), e2 = __ldg(sp + 2 * SJ + dhi);
-          row_scan<false>(X, b0, e0, i, x, r2c_hi, ph, fx, fy);
-          row_scan<true>(X, b1, e1, i, x, r2c_hi, ph, fx, fy);
-          row_scan<false>(X, b2, e2, i, x, r2c_hi, ph, fx, fy);
-        }
-        if (near_i) {   // the rare fourth and fifth row
-          const int* sl = a.start + ck - 2 * SJ;
-          const int* sh = a.start + ck + 2 * SJ;
-          row_scan<false>(X, __ldg(sl + dlo), __ldg(sl + dhi), i, x, r2c_hi, ph, fx, fy);
-          row_scan<false>(X, __ldg(sh + dlo), __ldg(sh + dhi), i, x, r2c_hi, ph, fx, fy);
-        }
+      if (staged) {
+        const int cr = ck - B.cA;
+        pair_search(&B.start[0][B.soff[0] + cr], &B.start[1][B.soff[1] + cr], &B.start[2][B.soff[2] + cr],
+                    &B.pos[0][0] + B.poff[0], &B.pos[1][0] + B.poff[1], &B.pos[2][0] + B.poff[2],
+                    X, a.start + ck, SJ, near_i, near_j, i, x, ph, fx, fy);
+      } else {
+        const int* gs = a.start + ck;
+        pair_search(gs - SJ, gs, gs + SJ, X, X, X, X, gs, SJ, near_i, near_j, i, x, ph, fx, fy);
       }
 
       force_walls(a, x, fx, fy);

@@ -202,7 +202,23 @@ int ptoy_find_blocks(ptoy_engine* h, const float* pos_xy, size_t n, int64_t* blo
  * strip boundary (or teleported) after the update.  N strips give bit-identical results to one
  * GPU.  Configure BEFORE adding particles; ptoy_add_particles then keeps only the particles of
  * the rank's own strip. */
-int ptoy_configure_strips(ptoy_engine* h, int rank, int world, const int32_t* col_begin /* world+1 */);
+int ptoy_configure_strips(ptoy_engine* h, int rank, int world, const int32_t* col_begin /* world+1 */,
+                          int ghost_rows, size_t id_capacity, int bonds);
+/*   ghost_rows   boundary sub-rows (0.04 each) mirrored on either side of a strip; 0 = the default 2,
+ *                which covers the pair force.  A bond partner must lie within the ghost zone of the
+ *                strip that holds the particle: scenes whose bonds stretch across a strip boundary
+ *                want 4 to 6 (a partner beyond it raises error bit 16).
+ *   id_capacity  1 + the largest particle id of the WHOLE scene (all strips): migrants and ghosts
+ *                carry ids this rank never loaded, and every id-indexed table must cover them.
+ *                0 = grow with the ids this rank sees (single-strip use, tests that load every
+ *                particle into every rank).
+ *   bonds        non-zero if ANY rank will set bonds: the halo then also carries particle ids and a
+ *                migrant takes its bond row (first 6 partners) along.  Must agree across ranks.
+ * While decomposed: ptoy_set_bonds / ptoy_set_frozen take the entries of this rank's own
+ * particles (more is allowed); bonds should be set before stepping (a later edit re-uploads the
+ * rank's host list and forgets rows that arrived with migrants); ptoy_get_bonds returns the
+ * rank's list without the CheckBonds pruning (whether a partner is gone is not a local question;
+ * the device skips dead partners either way); the block grid cannot grow. */
 /* One process per GPU: rank 0 creates the 128-byte id, every rank connects with it (collective). */
 int ptoy_nccl_unique_id(void* out128);
 int ptoy_nccl_connect(ptoy_engine* h, const void* uid128);
@@ -212,15 +228,23 @@ typedef struct ptoy_group ptoy_group;
 int ptoy_group_create(ptoy_group** out, ptoy_engine** engines, int n);
 int ptoy_group_step_n(ptoy_group* g, int n);
 void ptoy_group_destroy(ptoy_group* g);
-/* Sticky device-side error bits: 2 arrivals exceed capacity, 4 ghost slice exceeds capacity,
- * 8 a migrant outbox overflowed. */
+/* Sticky device-side error bits:
+ *    2  arriving migrants exceed the particle capacity        (PTOY_ERR_CAPACITY)
+ *    4  a boundary slice exceeds the ghost capacity           (PTOY_ERR_CAPACITY)
+ *    8  a migrant outbox overflowed (PTOY_MIGRANT_CAP)        (PTOY_ERR_CAPACITY)
+ *   16  a bond partner is neither local nor in a ghost row    (PTOY_ERR_DIST)
+ *   32  a migrant has more than 6 bonds: the rest of its row does not travel   (PTOY_ERR_CAPACITY)
+ *   64  an id beyond id_capacity arrived from another strip   (PTOY_ERR_DIST)
+ * Once a bit is set the simulation state is no longer trustworthy: ptoy_synchronize returns the
+ * error shown, and so do ptoy_step / ptoy_step_n as soon as the flag has reached the host (they
+ * do not wait for the device). */
 int ptoy_error_flags(ptoy_engine* h, int* flags);
 
 /* ---- measurement hooks -------------------------------------------------------------------- */
 
 /* Device time in ms of the kernels of the most recent ptoy_step_n(.., n), summed per
  * kernel kind over its launches, measured with CUDA events on the engine's stream.
- * kinds: 0 stage1, 1 stage2, 2 scan, 3 fill, 4 gather, 5 other.  Enable first. */
+ * kinds: 0 stage1, 1 stage2, 2 scan, 3 scatter, 4 fixup, 5 other.  Enable first. */
 int ptoy_enable_kernel_timing(ptoy_engine* h, int enable);
 int ptoy_get_kernel_times(ptoy_engine* h, double* ms6, int64_t* launches6);
 /* Number of kernel launches issued by this engine since creation. */

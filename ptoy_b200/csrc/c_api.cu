@@ -52,7 +52,7 @@ struct ptoy_group {
 extern "C" {
 
 const char* ptoy_last_error(void) { return ptoy::g_last_error.c_str(); }
-int ptoy_abi_version(void) { return 1; }
+int ptoy_abi_version(void) { return 2; }
 
 int ptoy_create(ptoy_engine** out, int device) {
   if (!out) { ptoy::set_last_error("null out pointer"); return PTOY_ERR_ARG; }
@@ -203,8 +203,9 @@ int ptoy_find_blocks(ptoy_engine* h, const float* pos, size_t n, int64_t* block)
 }
 // ---- strip decomposition -----------------------------------------------------------------
 
-int ptoy_configure_strips(ptoy_engine* h, int rank, int world, const int32_t* col_begin) {
-  PTOY_TRY(h, E.configure_strips(rank, world, col_begin))
+int ptoy_configure_strips(ptoy_engine* h, int rank, int world, const int32_t* col_begin, int ghost_rows,
+                          size_t id_capacity, int bonds) {
+  PTOY_TRY(h, E.configure_strips(rank, world, col_begin, ghost_rows, id_capacity, bonds != 0))
 }
 int ptoy_nccl_unique_id(void* out128) {
   try {

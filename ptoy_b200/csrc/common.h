@@ -16,7 +16,7 @@ namespace ptoy {
 
 constexpr int kMaxWalls = 16;
 constexpr int kThreads = 256;
-constexpr int kSlotNone = -1;   // id -> slot map entry of an id that is not stored (left the grid / never added)
+constexpr int kSlotNone = -0x7fffffff - 1;   // id -> slot map entry of an id that is not stored (left the grid / never added)
 
 // Sub-cell grid.  S = floor(2*t) + 4 with t = fl(fl(x - A)/bs) exactly as
 // blocks::FindBlock computes it (blocks.h:156-158).
@@ -31,9 +31,12 @@ struct GridDev {
   float tol;       // |w~ - w| bound used by the division-free binning (kernels.cu cell_of_fast)
   float wmax;      // largest |w| for which tol holds
   // Strip decomposition: this engine stores sub-rows [row0, row0 + SI) of the
-  // global padded sub-grid as local rows [0, SI); it OWNS local rows [own_lo, own_hi); the two
-  // local rows below / above hold nothing locally and are served from the neighbours' ghost
-  // slices.  A single-GPU engine is the case row0 = 0, own = [2, SI - 2): the global padding rows.
+  // global padded sub-grid as local rows [0, SI); it OWNS local rows [own_lo, own_hi).  The
+  // own_lo rows below and SI - own_hi rows above are GHOST rows: copies of the neighbour strips'
+  // boundary rows, installed every stage right before slot 0 (negative slots) and right behind
+  // the last owned particle, with start[] entries to match, so that a search window is one
+  // contiguous slot range whether it lies in owned or ghost rows.  A single-GPU engine is the
+  // case row0 = 0, own = [2, SI - 2): the (always empty) global padding rows.
   int row0;
   int own_lo, own_hi;
 };
@@ -44,17 +47,21 @@ struct DistDev {
   int world, rank;
   int row_begin[kMaxRanks + 1];
   // migrant outbox: one fixed-size block per destination rank, laid out as
-  //   int count (16 B header) | float2 pos[cap] | float2 vel[cap] | int id[cap] | int tag[cap]
-  // tag = old slot of the migrant on this rank: makes the receiver's order deterministic
+  //   int count (16 B header) | float2 pos[cap] | float2 vel[cap] | int id[cap] | int tag[cap] | int4 row[cap][2]
+  // tag = old slot of the migrant on this rank: makes the receiver's order deterministic;
+  // row = the migrant's bond row (bonds travel with their particle)
   char* out_base;          // nullptr: particles of other strips are simply dropped
   long long out_stride;
   int out_cap;
+  const int* bond_ell;     // bond table by id (nullptr: the scene has no bonds)
+  int* err;
 };
 __host__ __device__ inline long long mig_off_pos() { return 16; }
 __host__ __device__ inline long long mig_off_vel(int cap) { return 16 + 8ll * cap; }
 __host__ __device__ inline long long mig_off_id(int cap) { return 16 + 16ll * cap; }
 __host__ __device__ inline long long mig_off_tag(int cap) { return 16 + 20ll * cap; }
-__host__ __device__ inline long long mig_stride(int cap) { return 16 + 24ll * cap; }
+__host__ __device__ inline long long mig_off_row(int cap) { return 16 + 24ll * cap; }
+__host__ __device__ inline long long mig_stride(int cap) { return 16 + 56ll * cap; }
 
 // Physics constants, computed on the host with the reference's own expression
 // types (particles.cpp:7-24) so the bit patterns agree.
@@ -127,11 +134,6 @@ struct StageArgs {
   const int* id;
   const int* cell;       // sort key (local sub-row * SJ + sub-column) of every sorted particle
   const int* start;      // [ncell+2] exclusive prefix of sub-cell populations
-  // ghost slices of the left (0) / right (1) neighbour strip for this stage: positions of its two
-  // boundary sub-rows and the matching slice of its start[] (2*SJ+1 entries, absolute indices
-  // into ITS array; entry 0 is the index of the first ghost particle).  nullptr = no neighbour.
-  const float2* gpos[2];
-  const int* gstart[2];
   DistDev dist;
   float margin;          // extra search margin in sub-cell units; stage 2: its upper bound
   // stage 2 of the tile kernels: margin = min(margin, margin_base + margin_scale * *dmax), where
@@ -149,7 +151,7 @@ struct StageArgs {
   const int* bond_ell;         // bond table by id: 8 ints = first 6 partner ids (-1 pad), unused, degree
   int* bslot;                  // [cap][8] partner slots + degree: written by stage 1, read by stage 2
   int cap;                     // stride of the slot-major bslot array
-  int ghost_cap;               // decoding of ghost references in slot_of_id (GhostMapArgs)
+  int id_cap;                  // entries of the id-indexed tables (slot_of_id, bond_ell, frozen_bits)
   int* err;                    // sticky error bits (Counters::err_flags)
   // portals
   int n_sides;           // 2 * pairs
@@ -222,6 +224,10 @@ struct ArrivalArgs {   // migrants received from every source rank -> appended b
   int* cnt;
   unsigned long long* arr_vkey;
   int cap;
+  int rank;
+  int neighbours_only;      // only the blocks of rank - 1 / rank + 1 were exchanged this iteration
+  int* bond_ell;            // receiver's bond table by id (nullptr: no bonds); rows of the arrivals go in
+  int id_cap;
 };
 
 struct GhostPackArgs {   // boundary rows -> contiguous staging buffers for the neighbours
@@ -229,24 +235,41 @@ struct GhostPackArgs {   // boundary rows -> contiguous staging buffers for the 
   const float2* X;
   const int* start;
   int SJ;
+  int nrows;          // ghost rows per side (GridDev::own_lo)
   int row_lo[2];      // first local row of the slice sent to the left (0) / right (1) neighbour
   int ghost_cap;
-  float2* out_pos[2];
-  int* out_start[2];  // 2*SJ+1 entries, rebased to 0; nullptr = positions only (same layout as before)
+  float2* out_pos[2]; // [ghost_cap + 2]: the last element carries the sender's largest half-step drift
+  int* out_start[2];  // nrows*SJ+1 entries, rebased to 0; nullptr = positions only (same layout as before)
   const int* id;      // with out_id: particle ids of the same rows (bonds across strips)
   int* out_id[2];
+  const unsigned* dmax;
   int* err;
 };
 
-// Bonds across strips: the ids of the neighbours' boundary rows are entered into the id -> slot
-// map as ghost references  -2 - (side * ghost_cap + index)  so that a bond partner that lives in
-// a ghost row is found like a local one (kernels.cu bond_partner_pos).
-struct GhostMapArgs {
+// The neighbours' boundary rows become this strip's ghost rows: positions go right before slot 0
+// (left neighbour) / right behind the last owned particle (right neighbour), start[] of the ghost
+// rows is rewritten to match, and (bonds) the ghost ids enter the id -> slot map.
+struct GhostInstallArgs {
+  Counters* ctr;
+  int stage;                // 1: positions at x0 + start[] + ids; 2: positions at x_half + drift
+  int SJ, nrows, own_hi, ghost_cap;
+  const float2* in_pos[2];  // nullptr = no neighbour on that side
+  const int* in_start[2];
+  const int* in_id[2];      // nullptr: no bonds
+  float2* X;                // pos (stage 1) / pos_h (stage 2), slot 0
+  int* start;
   int* slot_of_id;
-  const int* ids[2];      // ghost ids per side
-  const int* gstart[2];   // ghost start slices: count = gstart[2*SJ] - gstart[0]
-  int* count[2];          // mark: written (remembered for the next unmark); unmark: read
-  int SJ, ghost_cap, mark;
+  int id_cap;
+  int* count[2];            // ghosts installed per side (for ghost_unmark)
+  int* err;
+};
+struct GhostUnmarkArgs {    // forget this iteration's ghosts in the id -> slot map (before the reorder)
+  const Counters* ctr;
+  int* slot_of_id;
+  int id_cap;
+  const int* in_id[2];
+  const int* count[2];
+  int ghost_cap;
 };
 
 // launchers (kernels.cu)
@@ -259,7 +282,8 @@ void launch_fixup(const ReorderArgs& a, int n_bound, cudaStream_t s);
 void launch_finalize(Counters* ctr, int* ticket, cudaStream_t s);
 void launch_arrivals(const ArrivalArgs& a, cudaStream_t s);
 void launch_ghost_pack(const GhostPackArgs& a, cudaStream_t s);
-void launch_ghost_map(const GhostMapArgs& a, cudaStream_t s);
+void launch_ghost_install(const GhostInstallArgs& a, cudaStream_t s);
+void launch_ghost_unmark(const GhostUnmarkArgs& a, cudaStream_t s);
 void launch_find_blocks(const GridDev& g, const float2* pos, size_t n, long long* out, cudaStream_t s);
 void launch_state_by_id(const GridDev& g, const Counters* ctr, const float2* pos, const float2* vel,
                         const int* id, int n_bound, float2* pos_by_id, float2* vel_by_id,

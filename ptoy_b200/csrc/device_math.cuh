@@ -186,42 +186,11 @@ __device__ __forceinline__ bool in_sorted(const int* __restrict__ list, int n, i
 // all forces on one particle (particles.cpp:839-910 calc_forces, :761-826 RHS_bonds,
 // :318-381 ApplyPortalsForces), summed in the reference's order of force kinds
 // ---------------------------------------------------------------------------------
-// Position of a bond partner given its entry in the id -> slot map: a local slot (>= 0), a ghost
-// reference -2 - (side * ghost_cap + index) into the neighbour strip's boundary rows, or -1
-// (partner left the grid: the bond is erased by CheckBonds, particles.cpp:205-215).
-template <bool STRIPS>
-__device__ __forceinline__ float2 bond_partner_pos(const StageArgs& a, const float2* __restrict__ X, int sb) {
-  if (sb >= 0) return __ldg(X + sb);
-  if (STRIPS && sb <= -2) {
-    const int code = -2 - sb;
-    const int side = code >= a.ghost_cap;
-    return __ldg(a.gpos[side] + (code - side * a.ghost_cap));
-  }
-  return make_float2(0.f, 0.f);
-}
-
-constexpr int kHitQueue = 6;     // pending in-range pairs per thread (shared memory)
-constexpr int kBondPlan = 6;     // bond partners per particle resolved up front / handed from stage 1 to stage 2
-struct HitQueue {
-  float dx[kHitQueue][kThreads];
-  float dy[kHitQueue][kThreads];
-};
-
-// One queued pair: the exact r^2 (reference rounding) decides, the prefilter only proposed it.
-__device__ __forceinline__ void eval_hit(const Phys& ph, float dx, float dy, float& fx, float& fy) {
-  const float r2 = dot2(dx, dy, dx, dy);
-  if (r2 < ph.r2c) {
-    float px, py;
-    pair_force(ph, dx, dy, r2, px, py);
-    fx = fadd(fx, px);
-    fy = fadd(fy, py);
-  }
-}
+constexpr int kBondPlan = 6;     // bond partners per particle held in the fixed-width bond table / handed from stage 1 to stage 2
 
 // FEAT selects what the scene uses, so that unused force kinds cost neither instructions nor
-// registers: 1 = bonds, 2 = portals, 4 = mouse point force / pick, 8 = strip decomposition
-// (ghost rows, ghost bond partners); launch_stage picks the variant.
-constexpr int kFeatBonds = 1, kFeatPortals = 2, kFeatExtras = 4, kFeatStrips = 8;
+// registers: 1 = bonds, 2 = portals, 4 = mouse point force / pick; launch_stage picks the variant.
+constexpr int kFeatBonds = 1, kFeatPortals = 2, kFeatExtras = 4;
 
 // particles.cpp:117-120: if (|v| > limit) v *= limit / |v|
 // fl(sqrt(v2)) > limit  <=>  v2 > v2c (sqrt is monotone; v2c found by bisection on the host), so
@@ -291,8 +260,17 @@ __device__ __forceinline__ void key_and_count(const GridDev& g, const DistDev& d
     if (k < d.out_cap) {
       reinterpret_cast<float2*>(blk + mig_off_pos())[k] = x;
       reinterpret_cast<float2*>(blk + mig_off_vel(d.out_cap))[k] = v;
-      reinterpret_cast<int*>(blk + mig_off_id(d.out_cap))[k] = id[slot];
+      const int pid = id[slot];
+      reinterpret_cast<int*>(blk + mig_off_id(d.out_cap))[k] = pid;
       reinterpret_cast<int*>(blk + mig_off_tag(d.out_cap))[k] = slot;
+      if (d.bond_ell) {   // bonds travel with their particle (rows longer than the table's 6 do not: flagged)
+        const int4* row = reinterpret_cast<const int4*>(d.bond_ell) + 2 * (size_t)pid;
+        int4* out = reinterpret_cast<int4*>(blk + mig_off_row(d.out_cap)) + 2 * (size_t)k;
+        const int4 r0 = row[0], r1 = row[1];
+        out[0] = r0;
+        out[1] = r1;
+        if (r1.w > 6) atomicOr(d.err, 32);
+      }
     }
   }
   newcell[slot] = key;

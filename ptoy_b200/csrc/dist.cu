@@ -78,13 +78,17 @@ struct NcclApi {
       throw Error(-5, std::string(#expr) + ": " + NcclApi::get().GetErrorString(r_));                \
   } while (0)
 
-void Engine::configure_strips(int rank, int world, const int* col_begin) {
+void Engine::configure_strips(int rank, int world, const int* col_begin, int ghost_rows, size_t id_capacity, bool bonds) {
   CUDA_CHECK(cudaSetDevice(device_));
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) throw Error(-2, "bad rank / world");
+  if (ghost_rows <= 0) ghost_rows = 2;
+  if (ghost_rows < 2 || ghost_rows > 64) throw Error(-2, "ghost_rows must be in [2, 64]");
   read_counters();
   if (h_ctr_->n_cur != 0) throw Error(-3, "configure_strips must precede add_particles");
   strip_.world = world;
   strip_.rank = rank;
+  strip_.ghost_rows = world > 1 ? ghost_rows : 2;
+  strip_.bonds = world > 1 && bonds;
   for (int r = 0; r <= world; ++r) strip_.col_begin[r] = col_begin ? col_begin[r] : 0;
   if (world > 1) {
     if (!col_begin || col_begin[0] != 0 || col_begin[world] != di_) throw Error(-2, "col_begin must run from 0 to dims.i");
@@ -92,27 +96,30 @@ void Engine::configure_strips(int rank, int world, const int* col_begin) {
       if (col_begin[r + 1] - col_begin[r] < 2) throw Error(-2, "a strip needs at least 2 block columns");
   }
   alloc_cells();
+  // every id-indexed table must cover the ids of ALL strips: migrants and ghosts bring ids this
+  // rank never loaded itself
+  if (id_capacity) ensure_id_capacity(id_capacity);
+  if (strip_.bonds) bonds_dirty_ = true;
   env_dirty_ = true;
 }
 
 void Engine::alloc_strip_buffers() {
   StripState& s = strip_;
-  // two boundary sub-rows hold about 2*SJ*1.2 particles at dense packing; allow 8 per sub-cell
-  s.ghost_cap = std::max(4096, 2 * grid_.SJ * 8);
-  s.out_cap = 1 << 16;
+  // the boundary sub-rows hold about ghost_rows*SJ*1.2 particles at dense packing; allow 8 per sub-cell
+  s.ghost_cap = std::max(4096, s.ghost_rows * grid_.SJ * 8);
+  s.out_cap = 1 << 14;
   if (const char* v = std::getenv("PTOY_MIGRANT_CAP")) s.out_cap = std::max(256, atoi(v));
-  const size_t nstart = 2 * (size_t)grid_.SJ + 1;
+  const size_t nstart = (size_t)s.ghost_rows * grid_.SJ + 1;
   for (int sd = 0; sd < 2; ++sd) {
-    s.send_pos[sd].alloc(s.ghost_cap);
+    s.send_pos[sd].alloc(s.ghost_cap + 2);
     s.send_start[sd].alloc(nstart);
-    s.ghost_pos[sd].alloc(s.ghost_cap);
-    s.ghost_pos_h[sd].alloc(s.ghost_cap);
+    s.ghost_pos[sd].alloc(s.ghost_cap + 2);
     s.ghost_start[sd].alloc(nstart);
+    CUDA_CHECK(cudaMemsetAsync(s.ghost_pos[sd].p, 0, (s.ghost_cap + 2) * sizeof(float2), stream_));
     CUDA_CHECK(cudaMemsetAsync(s.ghost_start[sd].p, 0, nstart * sizeof(int), stream_));
     CUDA_CHECK(cudaMemsetAsync(s.send_start[sd].p, 0, nstart * sizeof(int), stream_));
     s.send_id[sd].alloc(s.ghost_cap);
-    s.ghost_id[sd][0].alloc(s.ghost_cap);
-    s.ghost_id[sd][1].alloc(s.ghost_cap);
+    s.ghost_id[sd].alloc(s.ghost_cap);
   }
   s.ghost_n.alloc(2);
   CUDA_CHECK(cudaMemsetAsync(s.ghost_n.p, 0, 2 * sizeof(int), stream_));
@@ -132,6 +139,8 @@ DistDev Engine::make_dist(bool with_outbox) const {
   d.out_cap = strip_.out_cap;
   d.out_stride = mig_stride(strip_.out_cap);
   d.out_base = (with_outbox && strip_.world > 1) ? reinterpret_cast<char*>(strip_.outbox.p) : nullptr;
+  d.bond_ell = (strip_.world > 1 && has_bonds()) ? bond_ell_.p : nullptr;
+  d.err = &ctr_.p->err_flags;
   return d;
 }
 
@@ -143,7 +152,8 @@ void Engine::set_stream(cudaStream_t s) {
   owns_stream_ = false;
 }
 
-// Boundary rows -> staging buffers.  stage 1: positions at x0 + start[] slice; 2: x_half only.
+// Boundary rows -> staging buffers.  stage 1: positions at x0 + start[] slice (+ ids); 2: x_half
+// + this strip's largest half-step drift.
 void Engine::phase_pack_halo(int stage) {
   if (strip_.world == 1) return;
   GhostPackArgs g{};
@@ -151,15 +161,17 @@ void Engine::phase_pack_halo(int stage) {
   g.X = stage == 1 ? pos_[cur_].p : pos_h_.p;
   g.start = start_.p;
   g.SJ = grid_.SJ;
+  g.nrows = strip_.ghost_rows;
   g.row_lo[0] = grid_.own_lo;
-  g.row_lo[1] = grid_.own_hi - 2;
+  g.row_lo[1] = grid_.own_hi - strip_.ghost_rows;
   g.ghost_cap = strip_.ghost_cap;
   for (int sd = 0; sd < 2; ++sd) {
     g.out_pos[sd] = strip_.send_pos[sd].p;
     g.out_start[sd] = stage == 1 ? strip_.send_start[sd].p : nullptr;
-    g.out_id[sd] = (stage == 1 && !bonds_.empty()) ? strip_.send_id[sd].p : nullptr;
+    g.out_id[sd] = (stage == 1 && has_bonds()) ? strip_.send_id[sd].p : nullptr;
   }
   g.id = id_[cur_].p;
+  g.dmax = stage == 2 ? &ctr_.p->dmax : nullptr;
   g.err = &ctr_.p->err_flags;
   if (cap_ == 0) return;
   begin_timed(5);
@@ -167,29 +179,52 @@ void Engine::phase_pack_halo(int stage) {
   end_timed();
 }
 
-// After the stage-1 halo: enter the neighbours' boundary-row ids into the id -> slot map as ghost
-// references (and forget the previous iteration's), so bonds reach across the strip boundary.
-void Engine::phase_ghost_map() {
-  if (strip_.world == 1 || bonds_.empty()) return;
+// The received boundary rows become ghost rows: positions right before slot 0 / right behind the
+// last owned particle, start[] of the ghost rows to match, and (bonds) the ghost ids in the
+// id -> slot map, so that a bond partner in a ghost row is found like a local one.
+void Engine::phase_install_halo(int stage) {
+  if (strip_.world == 1 || cap_ == 0) return;
   StripState& s = strip_;
-  GhostMapArgs g{};
-  g.slot_of_id = slot_of_id_.p;
+  GhostInstallArgs g{};
+  g.ctr = ctr_.p;
+  g.stage = stage;
   g.SJ = grid_.SJ;
+  g.nrows = s.ghost_rows;
+  g.own_hi = grid_.own_hi;
   g.ghost_cap = s.ghost_cap;
-  for (int pass = 0; pass < 2; ++pass) {
-    g.mark = pass;
-    for (int sd = 0; sd < 2; ++sd) {
-      const bool have = sd == 0 ? s.rank > 0 : s.rank + 1 < s.world;
-      // unmark reads last iteration's ids, mark the ones just received
-      g.ids[sd] = have ? s.ghost_id[sd][pass ? s.ghost_cur : s.ghost_cur ^ 1].p : nullptr;
-      g.gstart[sd] = s.ghost_start[sd].p;
-      g.count[sd] = s.ghost_n.p + sd;
-    }
-    begin_timed(5);
-    launch_ghost_map(g, stream_);
-    end_timed();
+  for (int sd = 0; sd < 2; ++sd) {
+    const bool have = sd == 0 ? s.rank > 0 : s.rank + 1 < s.world;
+    g.in_pos[sd] = have ? s.ghost_pos[sd].p : nullptr;
+    g.in_start[sd] = s.ghost_start[sd].p;
+    g.in_id[sd] = (have && has_bonds()) ? s.ghost_id[sd].p : nullptr;
+    g.count[sd] = s.ghost_n.p + sd;
   }
-  s.ghost_cur ^= 1;
+  g.X = stage == 1 ? pos_[cur_].p : pos_h_.p;
+  g.start = start_.p;
+  g.slot_of_id = slot_of_id_.p;
+  g.id_cap = (int)id_cap_;
+  g.err = &ctr_.p->err_flags;
+  begin_timed(5);
+  launch_ghost_install(g, stream_);
+  end_timed();
+}
+
+void Engine::phase_unmark_halo() {
+  if (strip_.world == 1 || !has_bonds() || cap_ == 0) return;
+  StripState& s = strip_;
+  GhostUnmarkArgs g{};
+  g.ctr = ctr_.p;
+  g.slot_of_id = slot_of_id_.p;
+  g.id_cap = (int)id_cap_;
+  g.ghost_cap = s.ghost_cap;
+  for (int sd = 0; sd < 2; ++sd) {
+    const bool have = sd == 0 ? s.rank > 0 : s.rank + 1 < s.world;
+    g.in_id[sd] = have ? s.ghost_id[sd].p : nullptr;
+    g.count[sd] = s.ghost_n.p + sd;
+  }
+  begin_timed(5);
+  launch_ghost_unmark(g, stream_);
+  end_timed();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -209,6 +244,7 @@ struct LocalGroup : Transport {
       if (e[r]->device() != e[0]->device()) throw Error(-2, "a local group lives on one device");
       e[r]->set_stream(stream);
       e[r]->set_transport(nullptr);  // the group drives the phases itself
+      e[r]->set_local_group(true);   // (its migrant exchange is always all-to-all)
     }
   }
   ~LocalGroup() override {
@@ -221,18 +257,19 @@ struct LocalGroup : Transport {
     const int n = (int)e.size();
     for (int r = 0; r < n; ++r) {
       StripState& me = e[r]->strip_mut();
-      const size_t pb = (size_t)me.ghost_cap * sizeof(float2), sb = me.send_start[0].n * sizeof(int);
+      const size_t pb = (size_t)(me.ghost_cap + 2) * sizeof(float2), sb = me.send_start[0].n * sizeof(int);
+      const size_t ib = (size_t)me.ghost_cap * sizeof(int);
       if (r > 0) {  // my first rows -> left neighbour's right ghost
         StripState& l = e[r - 1]->strip_mut();
-        copy(stage == 1 ? l.ghost_pos[1].p : l.ghost_pos_h[1].p, me.send_pos[0].p, pb);
+        copy(l.ghost_pos[1].p, me.send_pos[0].p, pb);
         if (stage == 1) copy(l.ghost_start[1].p, me.send_start[0].p, sb);
-        if (stage == 1 && e[r]->has_bonds()) copy(l.ghost_id[1][l.ghost_cur].p, me.send_id[0].p, pb / 2);
+        if (stage == 1 && e[r]->has_bonds()) copy(l.ghost_id[1].p, me.send_id[0].p, ib);
       }
       if (r + 1 < n) {  // my last rows -> right neighbour's left ghost
         StripState& rr = e[r + 1]->strip_mut();
-        copy(stage == 1 ? rr.ghost_pos[0].p : rr.ghost_pos_h[0].p, me.send_pos[1].p, pb);
+        copy(rr.ghost_pos[0].p, me.send_pos[1].p, pb);
         if (stage == 1) copy(rr.ghost_start[0].p, me.send_start[1].p, sb);
-        if (stage == 1 && e[r]->has_bonds()) copy(rr.ghost_id[0][rr.ghost_cur].p, me.send_id[1].p, pb / 2);
+        if (stage == 1 && e[r]->has_bonds()) copy(rr.ghost_id[0].p, me.send_id[1].p, ib);
       }
     }
   }
@@ -253,11 +290,13 @@ struct LocalGroup : Transport {
       for (auto* x : e) x->phase_prepare();
       for (auto* x : e) x->phase_pack_halo(1);
       halo_all(1);
-      for (auto* x : e) x->phase_ghost_map();
+      for (auto* x : e) x->phase_install_halo(1);
       for (auto* x : e) x->phase_stage1();
       for (auto* x : e) x->phase_pack_halo(2);
       halo_all(2);
+      for (auto* x : e) x->phase_install_halo(2);
       for (auto* x : e) x->phase_stage2();
+      for (auto* x : e) x->phase_unmark_halo();
       migrants_all();
       for (auto* x : e) x->phase_reorder();
       for (auto* x : e) x->phase_end();
@@ -295,20 +334,21 @@ struct NcclTransport : Transport {
   }
   void halo(Engine& e, int stage) override {
     StripState& s = e.strip_mut();
-    const size_t pb = (size_t)s.ghost_cap * sizeof(float2), sb = s.send_start[0].n * sizeof(int);
+    const size_t pb = (size_t)(s.ghost_cap + 2) * sizeof(float2), sb = s.send_start[0].n * sizeof(int);
+    const size_t ib = (size_t)s.ghost_cap * sizeof(int);
     NCCL_CHECK(NcclApi::get().GroupStart());
     for (int sd = 0; sd < 2; ++sd) {
       const int peer = sd == 0 ? s.rank - 1 : s.rank + 1;
       if (peer < 0 || peer >= s.world) continue;
       // my boundary rows on side sd become the peer's ghost on its opposite side; symmetric recv
       NCCL_CHECK(NcclApi::get().Send(s.send_pos[sd].p, pb, ncclChar, peer, comm, e.stream()));
-      NCCL_CHECK(NcclApi::get().Recv(stage == 1 ? s.ghost_pos[sd].p : s.ghost_pos_h[sd].p, pb, ncclChar, peer, comm, e.stream()));
+      NCCL_CHECK(NcclApi::get().Recv(s.ghost_pos[sd].p, pb, ncclChar, peer, comm, e.stream()));
       if (stage == 1) {
         NCCL_CHECK(NcclApi::get().Send(s.send_start[sd].p, sb, ncclChar, peer, comm, e.stream()));
         NCCL_CHECK(NcclApi::get().Recv(s.ghost_start[sd].p, sb, ncclChar, peer, comm, e.stream()));
-        if (e.has_bonds()) {  // every rank holds the same bond set, so both ends agree
-          NCCL_CHECK(NcclApi::get().Send(s.send_id[sd].p, pb / 2, ncclChar, peer, comm, e.stream()));
-          NCCL_CHECK(NcclApi::get().Recv(s.ghost_id[sd][s.ghost_cur].p, pb / 2, ncclChar, peer, comm, e.stream()));
+        if (e.has_bonds()) {  // `bonds` was agreed at configure time, so both ends post the pair
+          NCCL_CHECK(NcclApi::get().Send(s.send_id[sd].p, ib, ncclChar, peer, comm, e.stream()));
+          NCCL_CHECK(NcclApi::get().Recv(s.ghost_id[sd].p, ib, ncclChar, peer, comm, e.stream()));
         }
       }
     }
@@ -317,10 +357,7 @@ struct NcclTransport : Transport {
   void migrants(Engine& e) override {
     StripState& s = e.strip_mut();
     const size_t st = (size_t)mig_stride(s.out_cap);
-    // Without portals a particle moves less than one sub-row per iteration, so it can only enter
-    // an adjacent strip: exchange with the two neighbours.  With portals a teleport can land on
-    // any strip: all-to-all.  (Every rank holds the same portal list, so both ends agree.)
-    const bool all_to_all = e.has_portals();
+    const bool all_to_all = !e.migrants_neighbours_only();   // (see engine.h)
     NCCL_CHECK(NcclApi::get().GroupStart());
     for (int r = 0; r < s.world; ++r) {
       if (r == s.rank) continue;

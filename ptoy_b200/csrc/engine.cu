@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <string>
 
 namespace ptoy {
 
@@ -58,29 +59,37 @@ static V2 seg_nearest(V2 A, V2 B, V2 p) {  // particles.h:37-46 / 67-77
 // ---- DevBuf ----------------------------------------------------------------------------
 template <class T>
 void DevBuf<T>::release() {
-  if (p) cudaFree(p);
+  if (p) cudaFree(p - head);
   p = nullptr;
   n = 0;
+  head = 0;
 }
 template <class T>
-void DevBuf<T>::alloc(size_t count) {
-  if (count <= n && p) return;
+void DevBuf<T>::alloc(size_t count, size_t head_room) {
+  if (count <= n && head_room <= head && p) return;
   release();
   if (count == 0) count = 1;
-  CUDA_CHECK(cudaMalloc((void**)&p, count * sizeof(T)));
+  T* raw = nullptr;
+  CUDA_CHECK(cudaMalloc((void**)&raw, (count + head_room) * sizeof(T)));
+  p = raw + head_room;
   n = count;
+  head = head_room;
 }
 template <class T>
-void DevBuf<T>::grow_keep(size_t count, cudaStream_t s) {
-  if (count <= n && p) return;
-  T* np = nullptr;
+void DevBuf<T>::grow_keep(size_t count, cudaStream_t s, size_t head_room) {
+  if (count <= n && head_room <= head && p) return;
+  count = std::max(count, n);
+  head_room = std::max(head_room, head);
+  T* raw = nullptr;
   if (count == 0) count = 1;
-  CUDA_CHECK(cudaMalloc((void**)&np, count * sizeof(T)));
-  if (p && n) CUDA_CHECK(cudaMemcpyAsync(np, p, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  CUDA_CHECK(cudaMalloc((void**)&raw, (count + head_room) * sizeof(T)));
+  T* np = raw + head_room;
+  if (p && n) CUDA_CHECK(cudaMemcpyAsync(np - head, p - head, (n + head) * sizeof(T), cudaMemcpyDeviceToDevice, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
-  if (p) cudaFree(p);
+  if (p) cudaFree(p - head);
   p = np;
   n = count;
+  head = head_room;
 }
 template struct DevBuf<float2>;
 template struct DevBuf<int>;
@@ -101,6 +110,9 @@ Engine::Engine(int device) : device_(device) {
   CUDA_CHECK(cudaSetDevice(device));
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CUDA_CHECK(cudaMallocHost((void**)&h_ctr_, sizeof(Counters)));
+  CUDA_CHECK(cudaMallocHost((void**)&h_err_, sizeof(int)));
+  *h_err_ = 0;
+  CUDA_CHECK(cudaEventCreateWithFlags(&err_event_, cudaEventDisableTiming));
   ctr_.alloc(1);
   ticket_.alloc(1);
   CUDA_CHECK(cudaMemsetAsync(ctr_.p, 0, sizeof(Counters), stream_));
@@ -127,6 +139,8 @@ Engine::~Engine() {
   for (auto& tl : timed_) { cudaEventDestroy(tl.a); cudaEventDestroy(tl.b); }
   for (auto ev : event_pool_) cudaEventDestroy(ev);
   if (h_ctr_) cudaFreeHost(h_ctr_);
+  if (h_err_) cudaFreeHost(h_err_);
+  if (err_event_) cudaEventDestroy(err_event_);
   delete transport_;
   if (stream_ && owns_stream_) cudaStreamDestroy(stream_);
 }
@@ -168,8 +182,11 @@ void Engine::alloc_cells() {
     for (int r = 0; r < strip_.world; ++r)
       if (strip_.row_begin[r + 1] - strip_.row_begin[r] < 4) throw Error(-2, "a strip needs at least 2 block columns");
   }
+  const int GR = strip_.world > 1 ? strip_.ghost_rows : 2;
   const int own_rows = strip_.row_begin[strip_.rank + 1] - strip_.row_begin[strip_.rank];
-  const long long SI = own_rows + 4;  // + two ghost rows on either side
+  for (int r = 0; r + 1 < strip_.world; ++r)
+    if (strip_.row_begin[r + 1] - strip_.row_begin[r] < GR) throw Error(-2, "a strip is narrower than the ghost zone");
+  const long long SI = own_rows + 2 * GR;  // + the ghost rows on either side
   const long long ncell = SI * SJ;
   if (ncell + 8 >= (1ll << 31)) throw Error(-4, "sub-cell grid exceeds 2^31 cells");
   if (SIg > 65535 || SJ > 65535) throw Error(-4, "block grid exceeds 32764 blocks per axis");
@@ -179,9 +196,9 @@ void Engine::alloc_cells() {
   grid_.fdi = (float)di_; grid_.fdj = (float)dj_;
   grid_.SI = (int)SI; grid_.SJ = (int)SJ;
   grid_.ncell = (int)ncell;
-  grid_.row0 = strip_.row_begin[strip_.rank] - 2;
-  grid_.own_lo = 2;
-  grid_.own_hi = (int)SI - 2;
+  grid_.row0 = strip_.row_begin[strip_.rank] - GR;
+  grid_.own_lo = GR;
+  grid_.own_hi = (int)SI - GR;
   grid_.inv_hsx = 2.0f / bs_.x;
   grid_.inv_hsy = 2.0f / bs_.y;
   grid_.wmax = (float)std::max(SIg, SJ) + 8.f;
@@ -211,15 +228,17 @@ void Engine::alloc_cells() {
 }
 
 void Engine::ensure_capacity(size_t n) {
-  if (n <= cap_) return;
-  size_t nc = std::max<size_t>(n, cap_ + cap_ / 2);
+  // strips: the ghost rows live right before slot 0 and right behind the last owned particle
+  const size_t gh = strip_.world > 1 ? (size_t)strip_.ghost_cap : 0;
+  if (n <= cap_ && pos_[0].head >= gh && pos_h_.head >= gh) return;
+  size_t nc = n <= cap_ ? cap_ : std::max<size_t>(n, cap_ + cap_ / 2);
   nc = (nc + 1023) / 1024 * 1024;
   for (int k = 0; k < 2; ++k) {
-    pos_[k].grow_keep(nc, stream_);
+    pos_[k].grow_keep(nc + gh, stream_, gh);
     vel_[k].grow_keep(nc, stream_);
     id_[k].grow_keep(nc, stream_);
   }
-  pos_h_.alloc(nc);
+  pos_h_.alloc(nc + gh, gh);
   vel_h_.alloc(nc);
   newcell_.alloc(nc);
   bslot_.alloc(nc * 8);
@@ -236,7 +255,7 @@ void Engine::ensure_id_capacity(size_t n) {
   const size_t old = slot_of_id_.n && slot_of_id_.p ? id_cap_ : 0;
   size_t nc = std::max<size_t>(n, id_cap_ + id_cap_ / 2);
   slot_of_id_.grow_keep(nc + 1, stream_);
-  launch_fill_i32(slot_of_id_.p + old, -1, nc + 1 - old, stream_);
+  launch_fill_i32(slot_of_id_.p + old, kSlotNone, nc + 1 - old, stream_);
   ++launches_;
   id_cap_ = nc;
   frozen_dirty_ = true;
@@ -252,10 +271,12 @@ void Engine::reset_scene(V2 A, V2 B) {
   frozen_.clear(); frozen_dirty_ = true;
   norend_buf_.clear();
   CUDA_CHECK(cudaMemsetAsync(ctr_.p, 0, sizeof(Counters), stream_));
+  *h_err_ = 0;
+  err_pending_ = false;
   n_bound_ = 0;
   removed_seen_ = 0;
   slot_map_valid_ = false;
-  if (slot_of_id_.p) { launch_fill_i32(slot_of_id_.p, -1, slot_of_id_.n, stream_); ++launches_; }
+  if (slot_of_id_.p) { launch_fill_i32(slot_of_id_.p, kSlotNone, slot_of_id_.n, stream_); ++launches_; }
   set_domain(A, B);
   rqA_ = A; rqB_ = B;
   reset_env_frame(A, B);
@@ -483,7 +504,7 @@ void Engine::sync_env() {
 void Engine::sync_bonds() {
   if (!bonds_dirty_) return;
   bonds_dirty_ = false;
-  if (bonds_.empty()) return;
+  if (!has_bonds()) return;   // (strips: a rank without bonds of its own still keeps the table for arrivals)
   int maxid = 0;
   for (auto& b : bonds_) maxid = std::max(maxid, std::max(b.first, b.second));
   ensure_id_capacity((size_t)maxid + 1);
@@ -502,10 +523,11 @@ void Engine::sync_bonds() {
   }
   bond_ell_.alloc(ell.size());
   bond_ptr_.alloc(ptr.size());
-  bond_col_.alloc(col.size());
+  bond_col_.alloc(col.size() + 1);
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   CUDA_CHECK(cudaMemcpy(bond_ptr_.p, ptr.data(), ptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  CUDA_CHECK(cudaMemcpy(bond_col_.p, col.data(), col.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (!col.empty())
+    CUDA_CHECK(cudaMemcpy(bond_col_.p, col.data(), col.size() * sizeof(int), cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(bond_ell_.p, ell.data(), ell.size() * sizeof(int), cudaMemcpyHostToDevice));
 }
 
@@ -524,7 +546,7 @@ void Engine::sync_frozen() {
 
 void Engine::ensure_slot_map() {
   if (slot_map_valid_ || id_cap_ == 0) return;
-  launch_fill_i32(slot_of_id_.p, -1, id_cap_ + 1, stream_);
+  launch_fill_i32(slot_of_id_.p, kSlotNone, id_cap_ + 1, stream_);
   launch_slot_map(ctr_.p, id_[cur_].p, n_bound_, slot_of_id_.p, stream_);
   launches_ += 2;
   slot_map_valid_ = true;
@@ -565,6 +587,10 @@ void Engine::toggle_bond(int a, int b) {
 // skipped by the force kernel from that iteration on; the host list is pruned lazily.
 void Engine::prune_bonds() {
   if (bonds_.empty()) return;
+  // Decomposed: a slot < 0 may be a particle of another strip, and `removed_total` counts
+  // migrants; whether a partner is gone is not a local question.  The device skips dead
+  // partners either way; the host list keeps them (documented in include/ptoy_b200.h).
+  if (strip_.world > 1) return;
   read_counters();
   if (h_ctr_->removed_total == removed_seen_) return;
   removed_seen_ = h_ctr_->removed_total;
@@ -573,7 +599,8 @@ void Engine::prune_bonds() {
   CUDA_CHECK(cudaMemcpyAsync(slot.data(), slot_of_id_.p, slot.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   auto dead = [&](const std::pair<int, int>& b) {
-    return (size_t)b.first >= id_cap_ || (size_t)b.second >= id_cap_ || slot[b.first] < 0 || slot[b.second] < 0;
+    return (size_t)b.first >= id_cap_ || (size_t)b.second >= id_cap_ || slot[b.first] == kSlotNone ||
+           slot[b.second] == kSlotNone;
   };
   bonds_.erase(std::remove_if(bonds_.begin(), bonds_.end(), dead), bonds_.end());
   bonds_dirty_ = true;
@@ -663,7 +690,7 @@ void Engine::upload_state(const float* pos, const float* vel, const int32_t* id,
   CUDA_CHECK(cudaMemcpyAsync(&ctr_.p->n_cur, &zero, sizeof(int), cudaMemcpyHostToDevice, stream_));
   n_bound_ = 0;
   slot_map_valid_ = false;
-  if (slot_of_id_.p && !bonds_.empty()) { launch_fill_i32(slot_of_id_.p, -1, id_cap_ + 1, stream_); ++launches_; }
+  if (slot_of_id_.p && has_bonds()) { launch_fill_i32(slot_of_id_.p, kSlotNone, id_cap_ + 1, stream_); ++launches_; }
   add_particles(pos, vel, id, n, false);
 }
 
@@ -680,7 +707,7 @@ void Engine::upload_state_async(const float* pos, const float* vel, const int32_
     ensure_capacity(n + (size_t)arrivals_bound());
     ensure_id_capacity((size_t)max_id + 1);
   }
-  if (slot_of_id_.p && !bonds_.empty()) { launch_fill_i32(slot_of_id_.p, -1, id_cap_ + 1, stream_); ++launches_; }
+  if (slot_of_id_.p && has_bonds()) { launch_fill_i32(slot_of_id_.p, kSlotNone, id_cap_ + 1, stream_); ++launches_; }
   launch_fill_i32(&ctr_.p->n_cur, (int)n, 1, stream_);
   ++launches_;
   n_bound_ = (int)n;
@@ -729,28 +756,23 @@ StageArgs Engine::make_stage_args(int stage) {
   a.pos_out = pos_[cur_].p; a.vel_out = vel_[cur_].p;
   a.id = id_[cur_].p;
   a.start = start_.p;
-  for (int sd = 0; sd < 2; ++sd) {
-    const bool have = strip_.world > 1 && (sd == 0 ? strip_.rank > 0 : strip_.rank + 1 < strip_.world);
-    a.gpos[sd] = have ? (stage == 1 ? strip_.ghost_pos[sd].p : strip_.ghost_pos_h[sd].p) : nullptr;
-    a.gstart[sd] = have ? strip_.ghost_start[sd].p : nullptr;
-  }
   a.dist = make_dist(true);
   a.margin = (stage == 1) ? margin1_ : margin2_;
   a.margin_base = margin2_base_;
   a.margin_scale = margin2_scale_;
-  a.dmax = strip_.world == 1 ? &ctr_.p->dmax : nullptr;  // (strips: the neighbours' drift is not known here)
+  a.dmax = &ctr_.p->dmax;
   a.has_frozen = !frozen_.empty();
   a.frozen_bits = frozen_bits_.p;
-  a.has_bonds = !bonds_.empty();
+  a.has_bonds = has_bonds();
   a.bond_ptr = bond_ptr_.p; a.bond_col = bond_col_.p; a.slot_of_id = slot_of_id_.p;
   a.bslot = bslot_.p; a.bond_ell = bond_ell_.p;
   a.cap = (int)cap_;
-  a.ghost_cap = strip_.ghost_cap;
+  a.id_cap = (int)id_cap_;
   a.err = &ctr_.p->err_flags;
   a.n_sides = has_portal_tables_ ? (int)portals_.size() * 2 : 0;
   a.sides = sides_.p; a.pblk_ptr = pblk_ptr_.p; a.pblk = pblk_.p;
   a.blk_flags = has_portal_tables_ ? blk_flags_.p : nullptr;
-  a.need_id = a.has_frozen || a.has_bonds || pick_enabled_;
+  a.need_id = a.has_frozen || a.has_bonds || pick_enabled_ || strip_.world > 1;
   a.force_out = nullptr;
   a.newcell = newcell_.p; a.cnt = cnt_.p;
   a.cell = cell_[cur_].p;
@@ -818,7 +840,7 @@ void Engine::reorder() {
   r.pos_out = pos_[cur_ ^ 1].p; r.vel_out = vel_[cur_ ^ 1].p; r.id_out = id_[cur_ ^ 1].p;
   r.rank = strip_.rank;
   r.arr_vkey = strip_.arr_vkey.p;
-  const bool keep_map = !bonds_.empty();
+  const bool keep_map = has_bonds();
   r.slot_of_id = keep_map ? slot_of_id_.p : nullptr;
   if (!keep_map) slot_map_valid_ = false;
   begin_timed(3);
@@ -860,7 +882,7 @@ void Engine::phase_prepare() {
   sync_env();
   sync_bonds();
   sync_frozen();
-  if (!bonds_.empty()) ensure_slot_map();
+  if (has_bonds()) ensure_slot_map();
   t_half_ = (float)((double)t_ + 0.5 * (double)dt_);                      // :126
   // The serial tail's resize decision (:157-175) depends on host state only, so it is
   // taken up front: if the block grid grows, portals are detected after the re-binning.
@@ -883,9 +905,8 @@ void Engine::phase_stage1() {
 }
 
 void Engine::phase_stage2() {
-  if (strip_.world > 1) {  // empty the migrant outbox headers
-    const size_t st = (size_t)mig_stride(strip_.out_cap);
-    for (int r = 0; r < strip_.world; ++r) CUDA_CHECK(cudaMemsetAsync(strip_.outbox.p + r * st, 0, 16, stream_));
+  if (strip_.world > 1) {  // empty the migrant outbox headers (one strided memset)
+    CUDA_CHECK(cudaMemset2DAsync(strip_.outbox.p, (size_t)mig_stride(strip_.out_cap), 0, 16, strip_.world, stream_));
   }
   if (n_bound_ <= 0) return;
   StageArgs a2 = make_stage_args(2);
@@ -914,6 +935,10 @@ void Engine::phase_reorder() {
     ar.newcell = newcell_.p; ar.cnt = cnt_.p;
     ar.arr_vkey = strip_.arr_vkey.p;
     ar.cap = (int)cap_;
+    ar.rank = strip_.rank;
+    ar.neighbours_only = migrants_neighbours_only();
+    ar.bond_ell = has_bonds() ? bond_ell_.p : nullptr;
+    ar.id_cap = (int)id_cap_;
     begin_timed(5);
     launch_arrivals(ar, stream_);
     end_timed();
@@ -941,27 +966,50 @@ void Engine::phase_end() {
 
 void Engine::iterate() {
   phase_prepare();
-  if (transport_) { phase_pack_halo(1); transport_->halo(*this, 1); phase_ghost_map(); }
+  if (transport_) { phase_pack_halo(1); transport_->halo(*this, 1); phase_install_halo(1); }
   phase_stage1();
-  if (transport_) { phase_pack_halo(2); transport_->halo(*this, 2); }
+  if (transport_) { phase_pack_halo(2); transport_->halo(*this, 2); phase_install_halo(2); }
   phase_stage2();
-  if (transport_) transport_->migrants(*this);
+  if (transport_) { phase_unmark_halo(); transport_->migrants(*this); }
   phase_reorder();
   phase_end();
 }
 
+// Sticky device error bits (include/ptoy_b200.h): the flags word is copied to pinned host memory
+// behind every batch of iterations; whoever looks next (without waiting, unless asked to) throws.
+void Engine::check_device_errors(bool wait) {
+  if (err_pending_) {
+    if (wait) CUDA_CHECK(cudaEventSynchronize(err_event_));
+    else if (cudaEventQuery(err_event_) != cudaSuccess) return;
+    err_pending_ = false;
+  }
+  const int f = *h_err_;
+  if (!f) return;
+  const int code = (f & (16 | 64)) ? -5 : -4;
+  throw Error(code, "device error flags " + std::to_string(f) +
+                        " (see ptoy_error_flags in include/ptoy_b200.h): the simulation state is no longer valid");
+}
 void Engine::step_to(float time_target) {
   CUDA_CHECK(cudaSetDevice(device_));
+  check_device_errors(false);
   while (t_ < time_target) iterate();                                    // :96 (quit = false)
+  CUDA_CHECK(cudaMemcpyAsync(h_err_, &ctr_.p->err_flags, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaEventRecord(err_event_, stream_));
+  err_pending_ = true;
 }
 void Engine::step_n(int n) {
   CUDA_CHECK(cudaSetDevice(device_));
+  check_device_errors(false);
   for (int i = 0; i < n; ++i) iterate();
+  CUDA_CHECK(cudaMemcpyAsync(h_err_, &ctr_.p->err_flags, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaEventRecord(err_event_, stream_));
+  err_pending_ = true;
 }
 void Engine::synchronize() {
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   CUDA_CHECK(cudaGetLastError());
+  check_device_errors(true);
 }
 
 // ---- read-back ------------------------------------------------------------------------------
@@ -1075,7 +1123,7 @@ void Engine::eval_forces(int stage, size_t id_cap, float* force) {
   if (stage != 1 && stage != 2) throw Error(-2, "stage must be 1 or 2");
   sync_env(); sync_bonds(); sync_frozen();
   read_counters();
-  if (!bonds_.empty()) ensure_slot_map();
+  if (has_bonds()) ensure_slot_map();
   force_dbg_.alloc(std::max<size_t>(cap_, 1));
   const size_t m = std::max(id_cap, id_cap_) + 1;
   DevBuf<float2> by_id;

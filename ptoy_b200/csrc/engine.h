@@ -27,10 +27,11 @@ struct PortalHost {
 
 template <class T>
 struct DevBuf {
-  T* p = nullptr;
+  T* p = nullptr;      // element 0; `head` more elements are addressable before it (ghost rows)
   size_t n = 0;
-  void alloc(size_t count);          // discards contents
-  void grow_keep(size_t count, cudaStream_t s);  // preserves the first n entries
+  size_t head = 0;
+  void alloc(size_t count, size_t head_room = 0);          // discards contents
+  void grow_keep(size_t count, cudaStream_t s, size_t head_room = 0);  // preserves [-head, n)
   void release();
   ~DevBuf() { release(); }
   DevBuf() = default;
@@ -44,14 +45,15 @@ struct StripState {
   int world = 1, rank = 0;
   int col_begin[kMaxRanks + 1] = {0};  // first block column (blocks::dims_.i index) of every rank
   int row_begin[kMaxRanks + 1] = {0};  // the same as global sub-rows
+  int ghost_rows = 2;                  // boundary sub-rows mirrored on either side (>= 2; wider for long bonds)
+  bool bonds = false;                  // the decomposed scene has bonds (agreed across ranks at configure time)
   int ghost_cap = 0, out_cap = 0;
-  DevBuf<float2> send_pos[2];          // my boundary rows for the left / right neighbour
+  DevBuf<float2> send_pos[2];          // my boundary rows for the left / right neighbour (+ drift in the last element)
   DevBuf<int> send_start[2];
-  DevBuf<float2> ghost_pos[2], ghost_pos_h[2];  // neighbours' boundary rows: at x0 / at x_half
+  DevBuf<float2> ghost_pos[2];         // neighbours' boundary rows as received (x0, then x_half)
   DevBuf<int> ghost_start[2];
-  DevBuf<int> send_id[2], ghost_id[2][2];  // ids of the boundary rows (bonds across strips); [side][cur/prev]
-  DevBuf<int> ghost_n;                     // [2] ghosts entered into the id -> slot map last iteration
-  int ghost_cur = 0;
+  DevBuf<int> send_id[2], ghost_id[2]; // ids of the boundary rows (bonds across strips)
+  DevBuf<int> ghost_n;                 // [2] ghosts installed per side this iteration
   DevBuf<unsigned char> outbox, inbox; // world blocks each (common.h DistDev layout)
   DevBuf<unsigned long long> arr_vkey;
 };
@@ -118,14 +120,15 @@ class Engine {
 
   // strip decomposition (dist.cu).  Phases of one iteration, so that a transport (in-process
   // group of strips, or NCCL between processes) can run the exchanges between them.
-  void configure_strips(int rank, int world, const int* col_begin);
+  void configure_strips(int rank, int world, const int* col_begin, int ghost_rows, size_t id_capacity, bool bonds);
   const StripState& strip() const { return strip_; }
   StripState& strip_mut() { return strip_; }
   void phase_prepare();        // host bookkeeping: dirty state -> device, resize decision
   void phase_pack_halo(int stage);   // boundary rows -> send buffers (stage 1: x0 + start slice, 2: x_half)
-  void phase_ghost_map();      // neighbours' boundary ids -> id -> slot map (bonds across strips)
+  void phase_install_halo(int stage);  // received boundary rows -> ghost rows (positions, start[], id -> slot map)
+  void phase_unmark_halo();    // ghosts leave the id -> slot map again (before the reorder)
   void phase_stage1();
-  bool has_bonds() const { return !bonds_.empty(); }
+  bool has_bonds() const { return !bonds_.empty() || (strip_.world > 1 && strip_.bonds); }
   bool has_portals() const { return !portals_.empty(); }
   void phase_stage2();
   void phase_reorder();        // arrivals + reorder
@@ -136,6 +139,7 @@ class Engine {
   void set_stream(cudaStream_t s);
   int device() const { return device_; }
   int error_flags();
+  void check_device_errors(bool wait);   // throws PTOY_ERR_CAPACITY / PTOY_ERR_DIST if a sticky error bit is set
 
   // measurement
   void enable_kernel_timing(bool e);
@@ -200,6 +204,9 @@ class Engine {
   unsigned epoch_ = 0;
   DevBuf<Counters> ctr_;
   Counters* h_ctr_ = nullptr;  // pinned
+  int* h_err_ = nullptr;       // pinned: err_flags as of the last completed iteration (async copy)
+  cudaEvent_t err_event_ = nullptr;
+  bool err_pending_ = false;
   DevBuf<int> slot_of_id_;
   bool slot_map_valid_ = false;
   DevBuf<uint32_t> frozen_bits_, bond_ptr_;
@@ -233,6 +240,14 @@ class Engine {
   void alloc_strip_buffers();
   DistDev make_dist(bool with_outbox) const;
   int arrivals_bound() const { return strip_.world > 1 ? strip_.world * strip_.out_cap : 0; }
+ public:
+  // Without portals a particle moves less than one sub-row per iteration, so it can only enter an
+  // adjacent strip: migrants are exchanged with the two neighbours only.  With portals a teleport can
+  // land on any strip: all-to-all.  (Every rank holds the same portal list, so all ends agree.)
+  bool migrants_neighbours_only() const { return !local_group_ && portals_.empty(); }
+  void set_local_group(bool v) { local_group_ = v; }
+ private:
+  bool local_group_ = false;
 
   // ---- helpers --------------------------------------------------------------------------
   void init_grid(V2 A, V2 B);                 // blocks::InitEmptyBlocks

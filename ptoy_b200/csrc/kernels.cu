@@ -7,387 +7,20 @@
 // the reference's; only the ORDER in which a particle's pair contributions are
 // summed differs (sub-cell order instead of block/slot order).
 //
-// Kernels (one launch each per iteration):
-//   stage_kernel<1>  forces at x0 + half kick/drift          particles.cpp:97-123
-//   stage_kernel<2>  forces at x_half + full update + portal teleport + new
-//                    sub-cell key + histogram                particles.cpp:128-153,177-179
-//   scan_kernel      single-pass decoupled look-back exclusive scan of the histogram
-//   fill_kernel      counting-sort slot assignment
-//   gather_kernel    deterministic (stable) reorder of pos/vel/id + id->slot map
+// Kernels of one iteration; the two stage kernels live in stage_tile.cuh:
+//   stage_tile_kernel<1>  forces at x0 + half kick/drift       particles.cpp:97-123
+//   stage_tile_kernel<2>  forces at x_half + full update + portal teleport + new sort key +
+//                         histogram                            particles.cpp:128-153,177-179
+//   scan_kernel           single-pass decoupled look-back exclusive scan of the histogram
+//   scatter_kernel        stable reorder of pos/vel/id in one pass (+ fixup_kernel for the few
+//                         cells whose order the scatter could not decide)
+// plus the strip decomposition's pack / install / arrival kernels and read-back helpers.
 #include <algorithm>
 
 #include "common.h"
 #include "device_math.cuh"
 
-// resident CTAs per SM the stage kernels are compiled for (measured on B200: 40 registers win
-// without bonds, 48 with the bond partner prefetch)
-#ifndef PTOY_STAGE_MINB
-#define PTOY_STAGE_MINB 6
-#endif
-#ifndef PTOY_STAGE_MINB_BONDS
-#define PTOY_STAGE_MINB_BONDS 5
-#endif
-
 namespace ptoy {
-
-template <int STAGE, int FEAT>
-__device__ __forceinline__ float2 particle_force(
-    const StageArgs& a, const float2* __restrict__ X, HitQueue& hq, int slot, int pid, float2 x, float2 v,
-    int Si, int Sj, float ui, float uj, int blk, unsigned flags) {
-  const Phys& ph = a.ph;
-  float fx = 0.0f, fy = 0.0f;
-  if (ph.gravity_enable) { fx = ph.gfx; fy = ph.gfy; }                       // :849-851
-
-  if ((FEAT & kFeatExtras) && ph.force_enabled) {                            // :854-863
-    const float rx = fsub(x.x, ph.fcx), ry = fsub(x.y, ph.fcy);
-    const float l = len2(rx, ry);
-    if (l > ph.radius) {
-      const double ld = (double)l;
-      float s;
-      if (ph.force_attractive) {
-        const double l3 = __dmul_rn(__dmul_rn(ld, ld), ld);                  // pow(l, 3)
-        s = __double2float_rn(__ddiv_rn((double)(-ph.point_force_attractive), l3));
-      } else {
-        const double l2 = __dmul_rn(ld, ld);
-        s = __double2float_rn(__ddiv_rn((double)ph.point_force, __dmul_rn(l2, l2)));  // pow(l, 4)
-      }
-      fx = fadd(fx, fmul(rx, s));
-      fy = fadd(fy, fmul(ry, s));
-    }
-  }
-
-  if ((FEAT & kFeatPortals) && (flags & 2u)) {                               // :866-871
-    for (int s = 0; s < a.n_sides; ++s) {
-      const PortalSide ps = a.sides[s];
-      float ex, ey;
-      lj_noclamp(ph.RRe, x.x, x.y, ps.ax, ps.ay, ex, ey);
-      fx = fadd(fx, ex); fy = fadd(fy, ey);
-      lj_noclamp(ph.RRe, x.x, x.y, ps.bx, ps.by, ex, ey);
-      fx = fadd(fx, ex); fy = fadd(fy, ey);
-    }
-  }
-
-  if ((FEAT & kFeatExtras) && ph.pick_enabled && pid == ph.pick_id) {        // :874-876, :751-759
-    const float dx = fsub(x.x, ph.pkx), dy = fsub(x.y, ph.pky);
-    const float r = len2(dx, dy);
-    const float k = fdiv(fsub(ph.pickR, r), ph.pickR);
-    const float s = fmul(ph.sigma_pick, k);
-    fx = fadd(fx, fmul(dx, s));
-    fy = fadd(fy, fmul(dy, s));
-  }
-
-  fx = fsub(fx, fmul(v.x, ph.diss));                                         // :880
-  fy = fsub(fy, fmul(v.y, ph.diss));
-
-  // ---- bonds, part 1: partner slots and positions, fetched before the pair search starts so
-  // the loads overlap it.  Stage 1 reads the particle's row of the bond table (8 ints per id: the
-  // first 6 partner ids in ascending = std::set order, the degree in the last; two 16-byte loads),
-  // resolves partner id -> slot with one batch of independent gathers and records the slots in
-  // one 32-byte sector per particle; stage 2 (same sorted order, same partners) reads them back
-  // with two 16-byte loads.
-  int nb = 0;
-  float2 bpos[kBondPlan];
-  int bslot[kBondPlan];
-  if (FEAT & kFeatBonds) {
-    int4* hand = reinterpret_cast<int4*>(a.bslot) + 2 * (size_t)slot;
-    if (STAGE == 1) {
-      const int4* row = reinterpret_cast<const int4*>(a.bond_ell) + 2 * (size_t)pid;
-      const int4 r0 = __ldg(row), r1 = __ldg(row + 1);
-      const int bcol[kBondPlan] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
-      nb = r1.w;
-#pragma unroll
-      for (int k = 0; k < kBondPlan; ++k) bslot[k] = (bcol[k] >= 0) ? a.slot_of_id[bcol[k]] : -1;
-      if (FEAT & kFeatStrips) {  // a partner that is neither local nor in a ghost row cannot be served
-        bool lost = false;
-#pragma unroll
-        for (int k = 0; k < kBondPlan; ++k) lost |= bcol[k] >= 0 && bslot[k] == -1;
-        if (lost) atomicOr(a.err, 16);
-      }
-      hand[0] = make_int4(bslot[0], bslot[1], bslot[2], bslot[3]);
-      hand[1] = make_int4(bslot[4], bslot[5], -1, nb);
-    } else {
-      const int4 r0 = hand[0], r1 = hand[1];
-      bslot[0] = r0.x; bslot[1] = r0.y; bslot[2] = r0.z; bslot[3] = r0.w; bslot[4] = r1.x; bslot[5] = r1.y;
-      nb = r1.w;
-    }
-#pragma unroll
-    for (int k = 0; k < kBondPlan; ++k) bpos[k] = bond_partner_pos<(FEAT & kFeatStrips) != 0>(a, X, bslot[k]);
-  }
-
-  // ---- pair forces (:884-900 + :598-606) over the sub-cell neighbourhood ----------------
-  // Candidates are only TESTED in the loop, with a cheap conservative prefilter
-  // (fma(dx,dx,dy*dy) against r2c grown by a few ulp); the few that pass are queued per thread
-  // in shared memory and evaluated afterwards with the reference's exact arithmetic, so the
-  // divergent force evaluation runs once per queued pair instead of once per loop iteration in
-  // which any lane had a hit.  The queue is FIFO: contributions are summed in candidate order.
-  // The particle itself (skipped by address in the reference) is excluded by splitting its own
-  // row's range around its slot.
-  {
-    const int t = threadIdx.x;
-    int nq = 0;
-    const int r_lo = Si - 1 - (ui < a.margin), r_hi = Si + 1 + (ui > 1.0f - a.margin);
-    const int c_lo = Sj - 1 - (uj < a.margin), c_hi = Sj + 1 + (uj > 1.0f - a.margin);
-    auto test = [&](float2 pq) {
-      const float dx = fsub(x.x, pq.x), dy = fsub(x.y, pq.y);
-      const float r2a = __fmaf_rn(dx, dx, dy * dy);
-      if (r2a < ph.r2c_hi) {
-        hq.dx[nq][t] = dx; hq.dy[nq][t] = dy;
-        if (++nq == kHitQueue) {
-#pragma unroll
-          for (int k = 0; k < kHitQueue; ++k) eval_hit(ph, hq.dx[k][t], hq.dy[k][t], fx, fy);
-          nq = 0;
-        }
-      }
-    };
-    auto scan = [&](const float2* __restrict__ P, int q, int end) {
-      for (; q + 1 < end; q += 2) {
-        const float2 p0 = __ldg(P + q), p1 = __ldg(P + q + 1);
-        test(p0);
-        test(p1);
-      }
-      if (q < end) test(__ldg(P + q));
-    };
-    if (!(FEAT & kFeatStrips) || (r_lo >= a.g.own_lo && r_hi < a.g.own_hi)) {
-      // (strips: taken by every particle whose search rows are all owned — all but the two
-      // boundary rows on each side)
-      // the three rows every particle needs: all six cell offsets are loaded before the first
-      // scan; the rare extra rows (fractional position within the margin of a cell edge) follow
-      const int* sp = a.start + (Si - 1) * a.g.SJ;
-      const int b0 = __ldg(sp + c_lo), e0 = __ldg(sp + c_hi + 1);
-      const int b1 = __ldg(sp + a.g.SJ + c_lo), e1 = __ldg(sp + a.g.SJ + c_hi + 1);
-      const int b2 = __ldg(sp + 2 * a.g.SJ + c_lo), e2 = __ldg(sp + 2 * a.g.SJ + c_hi + 1);
-      scan(X, b0, e0);
-      scan(X, b1, slot);
-      scan(X, slot + 1, e1);
-      scan(X, b2, e2);
-      if (r_lo < Si - 1) {
-        const int* s2 = a.start + (Si - 2) * a.g.SJ;
-        scan(X, __ldg(s2 + c_lo), __ldg(s2 + c_hi + 1));
-      }
-      if (r_hi > Si + 1) {
-        const int* s2 = a.start + (Si + 2) * a.g.SJ;
-        scan(X, __ldg(s2 + c_lo), __ldg(s2 + c_hi + 1));
-      }
-    } else {
-      // strips: the same row order (so that N strips sum in the order one GPU does); a row outside
-      // the owned range is a row of the neighbouring strip, served from its ghost slices
-      auto scan_row = [&](int R) {
-        if (R >= a.g.own_lo && R < a.g.own_hi) {
-          const int base = R * a.g.SJ;
-          const int beg = __ldg(a.start + base + c_lo), end = __ldg(a.start + base + c_hi + 1);
-          if (R == Si) {
-            scan(X, beg, slot);
-            scan(X, slot + 1, end);
-          } else {
-            scan(X, beg, end);
-          }
-        } else {
-          const int side = R >= a.g.own_hi;
-          const int* gs = a.gstart[side];
-          if (gs == nullptr) return;
-          const int base = (R - (side ? a.g.own_hi : a.g.own_lo - 2)) * a.g.SJ;
-          const int g0 = __ldg(gs);
-          scan(a.gpos[side], __ldg(gs + base + c_lo) - g0, __ldg(gs + base + c_hi + 1) - g0);
-        }
-      };
-      scan_row(Si - 1);
-      scan_row(Si);
-      scan_row(Si + 1);
-      if (r_lo < Si - 1) scan_row(Si - 2);
-      if (r_hi > Si + 1) scan_row(Si + 2);
-    }
-    for (int k = 0; k < nq; ++k) eval_hit(ph, hq.dx[k][t], hq.dy[k][t], fx, fy);
-  }
-
-  // ---- walls (:903-909); exact zero outside each wall's grown bbox ----------------
-  if (!(x.x > a.free_lox && x.x < a.free_hix && x.y > a.free_loy && x.y < a.free_hiy)) {
-    for (int k = 0; k < a.n_walls; ++k) {
-      const WallDev w = a.walls[k];
-      if (x.x >= w.lox && x.x <= w.hix && x.y >= w.loy && x.y <= w.hiy) {
-        float qx, qy, wx, wy;
-        seg_nearest(w.ax, w.ay, w.bx, w.by, x.x, x.y, qx, qy);
-        lj_noclamp(ph.RRw, x.x, x.y, qx, qy, wx, wy);
-        fx = fadd(fx, wx);
-        fy = fadd(fy, wy);
-      }
-    }
-  }
-
-  // ---- bonds, part 2 (:761-826): CSR row of this id, partners ascending ----------------
-  if (FEAT & kFeatBonds) {
-    auto one_bond = [&](int sb, float2 q) {
-      if (sb == -1) return;  // partner left the grid: bond erased by CheckBonds (:205-215)
-      float bx, by;
-      // p_pos.dist(q_pos) = |q - p| and F12_bond's |p - q| are the same float: the differences
-      // are exact negatives of each other, so one sqrt serves both (particles.cpp:731,779)
-      const float ddx = fsub(x.x, q.x), ddy = fsub(x.y, q.y);
-      const float dist = len2(ddx, ddy);
-      bool found = false;
-      if ((FEAT & kFeatPortals) && !(dist < ph.bond_cutoff)) {               // :784-819
-        for (int s = 0; s < a.n_sides; ++s) {
-          const PortalSide po = a.sides[s];
-          const PortalSide ot = a.sides[s ^ 1];
-          float p_lambda, p_offset, q_lambda, q_offset;
-          portal_coords(po, x.x, x.y, p_lambda, p_offset);
-          portal_coords(ot, q.x, q.y, q_lambda, q_offset);
-          if (p_lambda > 0.0f && p_lambda < 1.0f && q_lambda > 0.0f && q_lambda < 1.0f &&
-              fmul(p_offset, q_offset) < 0.0f &&
-              (double)fabsf(fsub(p_offset, q_offset)) < ph.bond_portal_reach) {
-            const float sign = (p_offset > 0.0f) ? 1.0f : -1.0f;
-            float jx, jy;
-            portal_image(ph, po, q_lambda, q_offset, sign, jx, jy);
-            bond_force(ph, x.x, x.y, jx, jy, bx, by);
-            found = true;  // no break: the last matching (pair, side) wins
-          }
-        }
-      }
-      if (!found) {                                                          // :727-736 inlined
-        float k = fsub(1.0f, div_by_bondR(dist, ph.bondR, ph.bond_y));
-        k = (k < -4.0f) ? -4.0f : k;
-        const float sk = fmul(ph.sigma_bond, k);
-        bx = fmul(ddx, sk);
-        by = fmul(ddy, sk);
-      }
-      fx = fadd(fx, bx);
-      fy = fadd(fy, by);
-    };
-#pragma unroll
-    for (int k = 0; k < kBondPlan; ++k) one_bond(bslot[k], bpos[k]);  // absent / dead partners are -1
-    if (nb > kBondPlan) {  // more partners than the plan holds: walk the rest of the CSR row
-      const unsigned e0 = __ldg(a.bond_ptr + pid), ne = __ldg(a.bond_ptr + pid + 1) - e0;
-      for (unsigned e = kBondPlan; e < ne; ++e) {
-        const int sb = a.slot_of_id[a.bond_col[e0 + e]];
-        one_bond(sb, bond_partner_pos<(FEAT & kFeatStrips) != 0>(a, X, sb));
-      }
-    }
-  }
-
-  // ---- cross-portal forces (:318-381) ------------------------------------------------
-  if ((FEAT & kFeatPortals) && (flags & 1u)) {
-    for (int s = 0; s < a.n_sides; ++s) {
-      const int lb = a.pblk_ptr[s], le = a.pblk_ptr[s + 1];
-      if (!in_sorted(a.pblk + lb, le - lb, blk)) continue;
-      const PortalSide po = a.sides[s];
-      const PortalSide ot = a.sides[s ^ 1];
-      float lambda_c, offset_c;
-      portal_coords(po, x.x, x.y, lambda_c, offset_c);
-      if (!(lambda_c > 0.0f && lambda_c < 1.0f)) continue;
-      // same-portal particles on the other side of the plane: subtract (:345-355)
-      for (int l = lb; l < le; ++l) {
-        int r0, r1, c0, c1;
-        block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
-        for (int Rg = r0; Rg <= r1; ++Rg) {
-          const int R = Rg - a.g.row0;  // strips: only locally stored rows (DESIGN.md §7 limitation)
-          if (R < a.g.own_lo || R >= a.g.own_hi) continue;
-          const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
-          for (int q = beg; q < end; ++q) {
-            const float2 nb = X[q];
-            float ln, on;
-            portal_coords(po, nb.x, nb.y, ln, on);
-            if (ln > 0.0f && ln < 1.0f && fmul(on, offset_c) < 0.0f) {
-              const float dx = fsub(x.x, nb.x), dy = fsub(x.y, nb.y);
-              const float r2 = dot2(dx, dy, dx, dy);
-              if (r2 < ph.r2c) {
-                float px, py;
-                pair_force(ph, dx, dy, r2, px, py);
-                fx = fsub(fx, px);
-                fy = fsub(fy, py);
-              }
-            }
-          }
-        }
-      }
-      // images of the partner portal's particles: add (:358-375)
-      const int ob = a.pblk_ptr[s ^ 1], oe = a.pblk_ptr[(s ^ 1) + 1];
-      const float sign = (offset_c > 0.0f) ? 1.0f : -1.0f;
-      for (int l = ob; l < oe; ++l) {
-        int r0, r1, c0, c1;
-        block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
-        for (int Rg = r0; Rg <= r1; ++Rg) {
-          const int R = Rg - a.g.row0;  // strips: only locally stored rows (DESIGN.md §7 limitation)
-          if (R < a.g.own_lo || R >= a.g.own_hi) continue;
-          const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
-          for (int q = beg; q < end; ++q) {
-            const float2 nb = X[q];
-            float oln, oon;
-            portal_coords(ot, nb.x, nb.y, oln, oon);
-            if (oln > 0.0f && oln < 1.0f && fmul(oon, offset_c) < 0.0f) {
-              float jx, jy;
-              portal_image(ph, po, oln, oon, sign, jx, jy);
-              const float dx = fsub(x.x, jx), dy = fsub(x.y, jy);
-              const float r2 = dot2(dx, dy, dx, dy);
-              if (r2 < ph.r2c) {
-                float px, py;
-                pair_force(ph, dx, dy, r2, px, py);
-                fx = fadd(fx, px);
-                fy = fadd(fy, py);
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-  return make_float2(fx, fy);
-}
-
-
-template <int STAGE, int FEAT>
-__global__ void __launch_bounds__(kThreads, (FEAT & kFeatBonds) ? PTOY_STAGE_MINB_BONDS : PTOY_STAGE_MINB) stage_kernel(const __grid_constant__ StageArgs a) {
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  if (i >= a.ctr->n_cur) return;
-  const float2 x0 = a.pos[i];
-  float2 v0 = a.vel[i];
-  float2 x, v;
-  if (STAGE == 1) { x = x0; v = v0; } else { x = a.pos_h[i]; v = a.vel_h[i]; }
-  const float2* __restrict__ X = (STAGE == 1) ? a.pos : (const float2*)a.pos_h;
-  __shared__ HitQueue hq;
-  // the sub-cell this particle was binned into (stored by the reorder), and its approximate
-  // fractional position inside it (only compared against the search margin)
-  const int ck = a.cell[i];
-  const int Si = ck / a.g.SJ, Sj = ck - Si * a.g.SJ;
-  const float ui = fsub(x0.x, a.g.Ax) * a.g.inv_hsx - (float)(Si + a.g.row0 - 4);
-  const float uj = fsub(x0.y, a.g.Ay) * a.g.inv_hsy - (float)(Sj - 4);
-  int blk = 0;
-  unsigned flags = 0u;
-  if ((FEAT & kFeatPortals) && a.blk_flags) { blk = block_of_s(a.g, Si + a.g.row0, Sj); flags = a.blk_flags[blk]; }
-  const int pid = a.need_id ? a.id[i] : 0;
-
-  float2 f = particle_force<STAGE, FEAT>(a, X, hq, i, pid, x, v, Si, Sj, ui, uj, blk, flags);
-
-  bool frozen = false;
-  if (a.has_frozen) frozen = (a.frozen_bits[pid >> 5] >> (pid & 31)) & 1u;
-  if (frozen) {                                                      // particles.cpp:828-837
-    v.x = fmul(v.x, 0.0f); v.y = fmul(v.y, 0.0f);
-    f.x = fmul(f.x, 0.0f); f.y = fmul(f.y, 0.0f);
-    v0.x = fmul(v0.x, 0.0f); v0.y = fmul(v0.y, 0.0f);  // velocity_tmp was saved after ApplyFrozen
-  }
-  if (a.force_out) a.force_out[i] = f;
-  if (!a.write_state) return;
-
-  const Phys& ph = a.ph;
-  if (STAGE == 1) {                                                  // particles.cpp:109-123
-    float vx = fadd(v.x, fmul(f.x, ph.c1));
-    float vy = fadd(v.y, fmul(f.y, ph.c1));
-    clamp_velocity(ph, vx, vy);
-    const float xh = fadd(x.x, fmul(fmul(vx, ph.dt), 0.5f));
-    const float yh = fadd(x.y, fmul(fmul(vy, ph.dt), 0.5f));
-    a.pos_h[i] = make_float2(xh, yh);
-    a.vel_h[i] = make_float2(vx, vy);
-  } else {                                                           // particles.cpp:140-153
-    float vx = fadd(v0.x, fmul(f.x, ph.c2));
-    float vy = fadd(v0.y, fmul(f.y, ph.c2));
-    clamp_velocity(ph, vx, vy);
-    float2 xn = make_float2(fadd(x0.x, fmul(vx, ph.dt)), fadd(x0.y, fmul(vy, ph.dt)));
-    float2 vn = make_float2(vx, vy);
-    if (a.do_tail) {
-      if ((FEAT & kFeatPortals) && (flags & 1u)) teleport(a, blk, xn, vn);
-      key_and_count(a.g, a.dist, xn, vn, a.id, i, a.newcell, a.cnt);
-    }
-    a.pos_out[i] = xn;
-    a.vel_out[i] = vn;
-  }
-}
 
 // Standalone teleport + key pass: used when the block grid changed between the
 // update and DetectPortals (particles.cpp:157-179) and for add_particles.
@@ -629,8 +262,10 @@ __global__ void __launch_bounds__(kThreads) arrivals_kernel(const __grid_constan
   const int t = blockIdx.x * kThreads + threadIdx.x;
   const int src = t / a.in_cap, k = t - src * a.in_cap;
   if (src >= a.world) return;
+  auto exchanged = [&](int r) { return r != a.rank && (!a.neighbours_only || r == a.rank - 1 || r == a.rank + 1); };
   int off = 0, total = 0, mine = 0;
   for (int r = 0; r < a.world; ++r) {
+    if (!exchanged(r)) continue;   // (its block was not received this iteration: stale)
     const int raw = *reinterpret_cast<const int*>(a.in_base + r * a.in_stride);
     if (raw > a.in_cap && t == 0) atomicOr(&a.ctr->err_flags, 8);  // a sender's outbox overflowed
     const int c = min(raw, a.in_cap);
@@ -645,30 +280,77 @@ __global__ void __launch_bounds__(kThreads) arrivals_kernel(const __grid_constan
   if (dst >= a.cap) { atomicOr(&a.ctr->err_flags, 2); return; }
   const char* blk = a.in_base + src * a.in_stride;
   const float2 x = reinterpret_cast<const float2*>(blk + mig_off_pos())[k];
+  const int pid = reinterpret_cast<const int*>(blk + mig_off_id(a.in_cap))[k];
   a.pos[dst] = x;
   a.vel[dst] = reinterpret_cast<const float2*>(blk + mig_off_vel(a.in_cap))[k];
-  a.id[dst] = reinterpret_cast<const int*>(blk + mig_off_id(a.in_cap))[k];
+  a.id[dst] = pid;
   a.arr_vkey[off + k] = ((unsigned long long)src << 32) |
                         (unsigned)reinterpret_cast<const int*>(blk + mig_off_tag(a.in_cap))[k];
+  if (a.bond_ell) {   // the migrant's bond row travels with it
+    if (pid < a.id_cap) {
+      const int4* row = reinterpret_cast<const int4*>(blk + mig_off_row(a.in_cap)) + 2 * (size_t)k;
+      int4* out = reinterpret_cast<int4*>(a.bond_ell) + 2 * (size_t)pid;
+      out[0] = row[0];
+      out[1] = row[1];
+    } else {
+      atomicOr(&a.ctr->err_flags, 64);
+    }
+  }
   bool migrant;
   const int key = cell_key(a.g, cell_of_fast(a.g, x), migrant);  // the sender routed it here
   a.newcell[dst] = key;
   atomicAdd(a.cnt + key, 1);
 }
 
-// Copy the two boundary sub-rows on each side into staging buffers (positions; optionally the
-// matching slice of start[], rebased to 0) for the neighbouring strips.
+// Copy the boundary sub-rows on each side into staging buffers (positions; optionally the
+// matching slice of start[], rebased to 0, and the ids) for the neighbouring strips.
 __global__ void __launch_bounds__(kThreads) ghost_pack_kernel(const __grid_constant__ GhostPackArgs a) {
   const int side = blockIdx.y;
   const int t = blockIdx.x * kThreads + threadIdx.x;
   const int c0 = a.row_lo[side] * a.SJ;
-  const int b0 = a.start[c0], b1 = a.start[c0 + 2 * a.SJ];
+  const int b0 = a.start[c0], b1 = a.start[c0 + a.nrows * a.SJ];
   if (t == 0 && b1 - b0 > a.ghost_cap) atomicOr(a.err, 4);
   if (t < b1 - b0 && t < a.ghost_cap) {
     a.out_pos[side][t] = a.X[b0 + t];
     if (a.out_id[side]) a.out_id[side][t] = a.id[b0 + t];
   }
-  if (a.out_start[side] && t <= 2 * a.SJ) a.out_start[side][t] = a.start[c0 + t] - b0;
+  if (a.out_start[side] && t <= a.nrows * a.SJ) a.out_start[side][t] = a.start[c0 + t] - b0;
+  if (t == 0) a.out_pos[side][a.ghost_cap] = make_float2(a.dmax ? __uint_as_float(*a.dmax) : 0.f, 0.f);
+}
+
+// Install the received boundary rows as ghost rows (see GhostInstallArgs).
+__global__ void __launch_bounds__(kThreads) ghost_install_kernel(const __grid_constant__ GhostInstallArgs a) {
+  const int side = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  if (a.in_pos[side] == nullptr) return;
+  const int nk = a.nrows * a.SJ;                       // keys of the ghost rows on this side
+  const int n = a.ctr->n_cur;
+  const int g = min(a.in_start[side][nk], a.ghost_cap);   // ghosts on this side (the slice is rebased to 0)
+  const int base = side == 0 ? -g : n;                  // slot of the first one
+  if (t < g) {
+    a.X[base + t] = a.in_pos[side][t];
+    if (a.stage == 1 && a.in_id[side]) {
+      const int pid = a.in_id[side][t];
+      if (pid >= 0 && pid < a.id_cap) a.slot_of_id[pid] = base + t; else atomicOr(a.err, 64);
+    }
+  }
+  if (a.stage == 1) {
+    if (t <= nk) a.start[(side == 0 ? 0 : a.own_hi * a.SJ) + t] = base + a.in_start[side][t];
+    if (t == 0) *a.count[side] = g;
+  } else if (t == 0) {   // the neighbour's largest half-step drift widens this strip's search margin too
+    atomicMax(&a.ctr->dmax, __float_as_uint(a.in_pos[side][a.ghost_cap].x));
+  }
+}
+
+// Before the reorder: the ghosts leave the id -> slot map again (a slot outside [0, n) is a ghost's).
+__global__ void __launch_bounds__(kThreads) ghost_unmark_kernel(const __grid_constant__ GhostUnmarkArgs a) {
+  const int side = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  if (a.in_id[side] == nullptr || t >= *a.count[side]) return;
+  const int pid = a.in_id[side][t];
+  if (pid < 0 || pid >= a.id_cap) return;
+  const int sl = a.slot_of_id[pid];
+  if (sl != kSlotNone && (sl < 0 || sl >= a.ctr->n_cur)) a.slot_of_id[pid] = kSlotNone;
 }
 
 // ---------------------------------------------------------------------------------
@@ -732,11 +414,6 @@ __global__ void fill_i32_kernel(int* p, int v, size_t n) {
 // ---------------------------------------------------------------------------------
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
-template <int FEAT>
-static void launch_stage_feat(int stage, const StageArgs& a, int n_bound, cudaStream_t s) {
-  if (stage == 1) stage_kernel<1, FEAT><<<grid_for(n_bound), kThreads, 0, s>>>(a);
-  else stage_kernel<2, FEAT><<<grid_for(n_bound), kThreads, 0, s>>>(a);
-}
 // tile-staged kernels, one translation unit per (bonds, portals) combination (stage_tile.cu)
 void launch_stage_tile_g0(int stage, bool extras, const StageArgs& a, int n_bound, cudaStream_t s);
 void launch_stage_tile_g1(int stage, bool extras, const StageArgs& a, int n_bound, cudaStream_t s);
@@ -746,27 +423,13 @@ void launch_stage_tile_g3(int stage, bool extras, const StageArgs& a, int n_boun
 void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s) {
   if (n_bound <= 0) return;
   const int feat = (a.has_bonds ? kFeatBonds : 0) | (a.n_sides > 0 ? kFeatPortals : 0) |
-                   ((a.ph.force_enabled || a.ph.pick_enabled) ? kFeatExtras : 0) |
-                   (a.dist.world > 1 ? kFeatStrips : 0);
-  if (!(feat & kFeatStrips)) {
-    const bool extras = (feat & kFeatExtras) != 0;
-    switch (feat & 3) {
-      case 0: launch_stage_tile_g0(stage, extras, a, n_bound, s); break;
-      case 1: launch_stage_tile_g1(stage, extras, a, n_bound, s); break;
-      case 2: launch_stage_tile_g2(stage, extras, a, n_bound, s); break;
-      default: launch_stage_tile_g3(stage, extras, a, n_bound, s); break;
-    }
-    return;
-  }
-  switch (feat) {
-    case 8: launch_stage_feat<8>(stage, a, n_bound, s); break;
-    case 9: launch_stage_feat<9>(stage, a, n_bound, s); break;
-    case 10: launch_stage_feat<10>(stage, a, n_bound, s); break;
-    case 11: launch_stage_feat<11>(stage, a, n_bound, s); break;
-    case 12: launch_stage_feat<12>(stage, a, n_bound, s); break;
-    case 13: launch_stage_feat<13>(stage, a, n_bound, s); break;
-    case 14: launch_stage_feat<14>(stage, a, n_bound, s); break;
-    default: launch_stage_feat<15>(stage, a, n_bound, s); break;
+                   ((a.ph.force_enabled || a.ph.pick_enabled) ? kFeatExtras : 0);
+  const bool extras = (feat & kFeatExtras) != 0;
+  switch (feat & 3) {
+    case 0: launch_stage_tile_g0(stage, extras, a, n_bound, s); break;
+    case 1: launch_stage_tile_g1(stage, extras, a, n_bound, s); break;
+    case 2: launch_stage_tile_g2(stage, extras, a, n_bound, s); break;
+    default: launch_stage_tile_g3(stage, extras, a, n_bound, s); break;
   }
 }
 void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s) {
@@ -788,31 +451,18 @@ void launch_fixup(const ReorderArgs& a, int n_bound, cudaStream_t s) {
   const unsigned grid = (unsigned)std::min<size_t>(grid_for(n_bound), 148 * 4);
   fixup_kernel<<<grid, kThreads, 0, s>>>(a);
 }
-__global__ void __launch_bounds__(kThreads) ghost_map_kernel(const __grid_constant__ GhostMapArgs a) {
-  const int side = blockIdx.y;
-  const int t = blockIdx.x * kThreads + threadIdx.x;
-  if (a.ids[side] == nullptr) return;
-  if (a.mark) {
-    const int n = min(a.gstart[side][2 * a.SJ] - a.gstart[side][0], a.ghost_cap);
-    if (t == 0) *a.count[side] = n;
-    if (t < n) a.slot_of_id[a.ids[side][t]] = -2 - (side * a.ghost_cap + t);
-  } else {
-    // forget last iteration's ghosts (an id that became local meanwhile holds a slot >= 0: keep it)
-    if (t < *a.count[side]) {
-      const int pid = a.ids[side][t];
-      if (a.slot_of_id[pid] <= -2) a.slot_of_id[pid] = -1;
-    }
-  }
+void launch_ghost_install(const GhostInstallArgs& a, cudaStream_t s) {
+  const size_t n = (size_t)max(a.ghost_cap, a.nrows * a.SJ + 1);
+  ghost_install_kernel<<<dim3(grid_for(n), 2), kThreads, 0, s>>>(a);
 }
-
-void launch_ghost_map(const GhostMapArgs& a, cudaStream_t s) {
-  ghost_map_kernel<<<dim3(grid_for((size_t)a.ghost_cap), 2), kThreads, 0, s>>>(a);
+void launch_ghost_unmark(const GhostUnmarkArgs& a, cudaStream_t s) {
+  ghost_unmark_kernel<<<dim3(grid_for((size_t)a.ghost_cap), 2), kThreads, 0, s>>>(a);
 }
 void launch_arrivals(const ArrivalArgs& a, cudaStream_t s) {
   arrivals_kernel<<<grid_for((size_t)a.world * a.in_cap), kThreads, 0, s>>>(a);
 }
 void launch_ghost_pack(const GhostPackArgs& a, cudaStream_t s) {
-  const size_t n = (size_t)max(a.ghost_cap, 2 * a.SJ + 1);
+  const size_t n = (size_t)max(a.ghost_cap, a.nrows * a.SJ + 1);
   ghost_pack_kernel<<<dim3(grid_for(n), 2), kThreads, 0, s>>>(a);
 }
 void launch_finalize(Counters* ctr, int* ticket, cudaStream_t s) {

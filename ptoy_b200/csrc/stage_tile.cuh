@@ -500,7 +500,14 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
           const int bcol[kBondPlan] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
           nb = r1.w;
 #pragma unroll
-          for (int k = 0; k < kBondPlan; ++k) bslot[k] = (bcol[k] >= 0) ? a.slot_of_id[bcol[k]] : kSlotNone;
+          for (int k = 0; k < kBondPlan; ++k)
+            bslot[k] = ((unsigned)bcol[k] < (unsigned)a.id_cap) ? a.slot_of_id[bcol[k]] : kSlotNone;
+          if (a.dist.world > 1) {  // strips: a partner that is neither local nor in a ghost row cannot be served
+            bool lost = false;
+#pragma unroll
+            for (int k = 0; k < kBondPlan; ++k) lost |= bcol[k] >= 0 && bslot[k] == kSlotNone;
+            if (lost) atomicOr(a.err, 16);
+          }
           hand[0] = make_int4(bslot[0], bslot[1], bslot[2], bslot[3]);
           hand[1] = make_int4(bslot[4], bslot[5], kSlotNone, nb);
         } else {
@@ -534,7 +541,8 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
         if (nb > kBondPlan) {  // more partners than the plan holds: walk the rest of the CSR row
           const unsigned e0 = __ldg(a.bond_ptr + pid), ne = __ldg(a.bond_ptr + pid + 1) - e0;
           for (unsigned e = kBondPlan; e < ne; ++e) {
-            const int sb = a.slot_of_id[a.bond_col[e0 + e]];
+            const int pc = a.bond_col[e0 + e];
+            const int sb = ((unsigned)pc < (unsigned)a.id_cap) ? a.slot_of_id[pc] : kSlotNone;
             force_one_bond<FEAT>(a, x, sb, sb != kSlotNone ? __ldg(X + sb) : make_float2(0.f, 0.f), fx, fy);
           }
         }
@@ -545,7 +553,7 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
       // ---- ApplyFrozen + integrator --------------------------------------------------------------
       float2 f = make_float2(fx, fy);
       bool frozen = false;
-      if (a.has_frozen) frozen = (a.frozen_bits[pid >> 5] >> (pid & 31)) & 1u;
+      if (a.has_frozen && (unsigned)pid < (unsigned)a.id_cap) frozen = (a.frozen_bits[pid >> 5] >> (pid & 31)) & 1u;
       if (frozen) {                                                      // particles.cpp:828-837
         v.x = fmul(v.x, 0.0f); v.y = fmul(v.y, 0.0f);
         f.x = fmul(f.x, 0.0f); f.y = fmul(f.y, 0.0f);

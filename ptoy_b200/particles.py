@@ -80,7 +80,7 @@ SIGNATURES = {
     "ptoy_eval_forces": [_i, _sz, _f32p],
     "ptoy_id_capacity": [_szp],
     "ptoy_find_blocks": [_f32p, _sz, _i64p],
-    "ptoy_configure_strips": [_i, _i, _i32p],
+    "ptoy_configure_strips": [_i, _i, _i32p, _i, _sz, _i],
     "ptoy_nccl_connect": [_vp],
     "ptoy_error_flags": [_ip],
     "ptoy_enable_kernel_timing": [_i],
@@ -529,14 +529,15 @@ class Particles:
         return out[:len(pos)]
 
     # ------------------------------------------------------------------ strips (multi-GPU)
-    def configure_strips(self, rank, world, col_begin=None):
+    def configure_strips(self, rank, world, col_begin=None, ghost_rows=0, id_capacity=0, bonds=False):
         """Own block columns [col_begin[rank], col_begin[rank+1]) of the current grid.  Call after
-        reset_scene and before add_particles; add_particles then keeps only this strip's particles."""
+        reset_scene and before add_particles; add_particles then keeps only this strip's particles.
+        ghost_rows / id_capacity / bonds: see include/ptoy_b200.h ptoy_configure_strips."""
         if col_begin is None:
             col_begin = partition_columns(self.geometry()["dims"][0], world)
         cb = np.ascontiguousarray(col_begin, dtype=np.int32)
         assert len(cb) == world + 1
-        self._call("ptoy_configure_strips", int(rank), int(world), cb)
+        self._call("ptoy_configure_strips", int(rank), int(world), cb, int(ghost_rows), int(id_capacity), int(bool(bonds)))
         self.rank, self.world, self.col_begin = int(rank), int(world), cb
 
     def nccl_connect(self, uid):
@@ -620,14 +621,15 @@ class StripGroup:
     device-to-device copies in place of NCCL (include/ptoy_b200.h ptoy_group_*).  The test
     vehicle of the multi-GPU path: N virtual strips must equal one engine bit for bit."""
 
-    def __init__(self, domain, world, device=0, col_begin=None, gravity=(True, (0.0, -10.0))):
+    def __init__(self, domain, world, device=0, col_begin=None, gravity=(True, (0.0, -10.0)),
+                 ghost_rows=0, id_capacity=0, bonds=False):
         self.L = load_library()
         self.parts = []
         for r in range(world):
             p = Particles(device=device, default_scene=False)
             p.reset_scene(domain)
             p.set_gravity(*gravity)
-            p.configure_strips(r, world, col_begin)
+            p.configure_strips(r, world, col_begin, ghost_rows, id_capacity, bonds)
             p.set_renderer_ready(False)
             self.parts.append(p)
         arr = (C.c_void_p * world)(*[p.h for p in self.parts])

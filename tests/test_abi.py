@@ -39,7 +39,7 @@ def test_python_binding_covers_the_header(lib):
 
 
 def test_abi_version(lib):
-    assert lib.ptoy_abi_version() == 1
+    assert lib.ptoy_abi_version() == 2
 
 
 def test_no_gpu_means_loud_failure(lib):

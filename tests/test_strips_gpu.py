@@ -23,8 +23,8 @@ def single(sc, steps, setup=None):
     return g.state_by_id(sc.n), g.num_particles
 
 
-def strips(sc, steps, world, col_begin=None, setup=None):
-    grp = ptoy_b200.StripGroup(sc.domain, world, col_begin=col_begin, gravity=sc.gravity)
+def strips(sc, steps, world, col_begin=None, setup=None, **kw):
+    grp = ptoy_b200.StripGroup(sc.domain, world, col_begin=col_begin, gravity=sc.gravity, **kw)
     grp.add_particles(sc.pos, sc.vel, sc.ids)
     if setup:
         grp.each(setup)
@@ -119,6 +119,42 @@ def test_strips_with_bonds_across_the_boundaries(world):
         p.set_bonds(sc.bonds)
         p.set_frozen(sc.frozen)
     ref, n_ref = single(sc, 40, setup)
-    got, n_got = strips(sc, 40, world, setup=setup)
+    got, n_got = strips(sc, 40, world, setup=setup, bonds=True)
+    assert n_got == n_ref == sc.n
+    assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])
+
+
+@pytest.mark.parametrize("world,ghost_rows", [(2, 2), (3, 4)])
+def test_bond_rows_travel_with_their_particle(world, ghost_rows):
+    """Every strip is given ONLY the bond rows and frozen ids of the particles it holds at the
+    start (as a rank of a large decomposed scene would): a particle that moves to another strip
+    takes its bond row along, and the result still equals the single engine bit for bit."""
+    sc = scenes.hex_lattice(24000, 2.02, 0.01, seed=33, vel_scale=1.0)
+    sc.vel[:, 0] += np.float32(4.0)      # the whole sheet drifts in x, across the strip boundaries
+    scenes.add_lattice_bonds(sc)
+
+    def setup(p):
+        p.set_bonds(sc.bonds)
+        p.set_frozen(sc.frozen)
+    ref, n_ref = single(sc, 60, setup)
+
+    grp = ptoy_b200.StripGroup(sc.domain, world, gravity=sc.gravity, ghost_rows=ghost_rows, id_capacity=sc.n,
+                               bonds=True)
+    grp.add_particles(sc.pos, sc.vel, sc.ids)
+    moved = 0
+    owner0 = np.full(sc.n, -1)
+    for r, p in enumerate(grp.parts):
+        mine = p.state_by_id(sc.n)["block"] >= 0
+        owner0[mine] = r
+        p.set_bonds(sc.bonds[mine[sc.bonds[:, 0]]])
+        p.set_frozen(sc.frozen)          # (the frozen set is a bit mask by id: every rank takes all of it)
+    grp.step_n(60)
+    for r, p in enumerate(grp.parts):
+        moved += int(((p.state_by_id(sc.n)["block"] >= 0) & (owner0 != r)).sum())
+    got, n_got = grp.state_by_id(sc.n), grp.num_particles
+    flags = [p.error_flags for p in grp.parts]
+    grp.close()
+    assert not any(flags), flags
+    assert moved > 50, moved             # bonded particles did change strips
     assert n_got == n_ref == sc.n
     assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])

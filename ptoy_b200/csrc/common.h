@@ -159,6 +159,10 @@ struct StageArgs {
   const int* pblk_ptr;   // [n_sides+1] into pblk
   const int* pblk;       // Portal::blocks, ascending
   const uint8_t* blk_flags;  // per reference block: bit0 in a portal list, bit1 near a portal end
+  // strips: the particles of every listed portal block, gathered from the strips that own them
+  // (PortalZoneArgs): entry l of pblk holds zcnt[l] particles at X[zoff + l * kZoneCap ...]
+  const int* zcnt;       // nullptr: one strip, the blocks are read in place
+  int zoff;
   int need_id;
   // outputs
   float2* force_out;     // optional, by slot
@@ -272,7 +276,34 @@ struct GhostUnmarkArgs {    // forget this iteration's ghosts in the id -> slot 
   int ghost_cap;
 };
 
+// Cross-portal forces and through-portal bonds across strips (particles.cpp:318-381, 784-819):
+// every strip copies the particles of the portal blocks it owns - in the order the single-GPU
+// loop visits them: block-list entry, sub-row, slot - into a fixed-capacity table behind the
+// ghost rows of the position array; the tables are summed over the strips (each entry has one
+// owner, the others hold zeros), so every strip ends up with all portal-zone particles in the
+// same order and the forces stay bit-identical to one GPU.
+constexpr int kZoneCap = 24;   // particles per listed portal block
+struct PortalZoneArgs {
+  GridDev g;
+  const Counters* ctr;
+  const float2* X_in;     // pos (stage 1) / pos_h (stage 2), slot 0
+  float2* X;              // the same array: the table goes to X[zoff ...]
+  const int* id;
+  const int* start;
+  const int* pblk;
+  int n_entries;          // pblk_ptr[n_sides]
+  int zoff;
+  int* zcnt;              // [n_entries]
+  int* zid;               // [n_entries * kZoneCap]
+  int* slot_of_id;        // mark / unmark (bonds): zone particles that are neither local nor ghosts
+  int id_cap;
+  int* err;
+};
+
 // launchers (kernels.cu)
+void launch_zone_pack(const PortalZoneArgs& a, cudaStream_t s);
+void launch_zone_mark(const PortalZoneArgs& a, int mark, cudaStream_t s);
+void launch_sum_i32(int* dst, const int* src, size_t n, cudaStream_t s);
 void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s);
 void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s);
 void launch_scan(int* cnt, int* start, int n_items, int ncell, unsigned long long* tile_state,

@@ -37,6 +37,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   static NcclApi& get() {
     static NcclApi api = load();
@@ -60,6 +61,7 @@ struct NcclApi {
     a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
     a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
     a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
     return a;
   }
@@ -209,7 +211,65 @@ void Engine::phase_install_halo(int stage) {
   end_timed();
 }
 
+// ---- portal zones: cross-portal forces and through-portal bonds across strips ------------------
+static PortalZoneArgs zone_args(Engine& e, const GridDev& g, Counters* ctr, float2* X, const int* id, const int* start,
+                                const int* pblk, int n_entries, size_t zoff, int* zcnt, int* zid, int* slot_of_id,
+                                size_t id_cap) {
+  PortalZoneArgs z{};
+  z.g = g;
+  z.ctr = ctr;
+  z.X_in = X; z.X = X;
+  z.id = id; z.start = start; z.pblk = pblk;
+  z.n_entries = n_entries;
+  z.zoff = (int)zoff;
+  z.zcnt = zcnt; z.zid = zid;
+  z.slot_of_id = slot_of_id;
+  z.id_cap = (int)id_cap;
+  z.err = &ctr->err_flags;
+  (void)e;
+  return z;
+}
+
+void Engine::zone_buffers(int stage, int** pos_i32, size_t* n_pos, int** cnt, size_t* n_cnt, int** ids, size_t* n_ids) {
+  float2* X = stage == 1 ? pos_[cur_].p : pos_h_.p;
+  *pos_i32 = reinterpret_cast<int*>(X + zone_off());
+  *n_pos = (size_t)zone_entries_ * kZoneCap * 2;
+  *cnt = zcnt_.p; *n_cnt = (size_t)zone_entries_;
+  *ids = zid_.p; *n_ids = (size_t)zone_entries_ * kZoneCap;
+}
+
+void Engine::phase_pack_zones(int stage) {
+  if (!has_zones()) return;
+  int *zp, *zc, *zi;
+  size_t np, nc, ni;
+  zone_buffers(stage, &zp, &np, &zc, &nc, &zi, &ni);
+  CUDA_CHECK(cudaMemsetAsync(zp, 0, np * sizeof(int), stream_));
+  CUDA_CHECK(cudaMemsetAsync(zc, 0, nc * sizeof(int), stream_));
+  CUDA_CHECK(cudaMemsetAsync(zi, 0, ni * sizeof(int), stream_));
+  PortalZoneArgs z = zone_args(*this, grid_, ctr_.p, stage == 1 ? pos_[cur_].p : pos_h_.p, id_[cur_].p, start_.p, pblk_.p,
+                               zone_entries_, zone_off(), zcnt_.p, zid_.p, slot_of_id_.p, id_cap_);
+  begin_timed(5);
+  launch_zone_pack(z, stream_);
+  end_timed();
+}
+
+void Engine::phase_mark_zones(int stage) {
+  if (!has_zones() || !has_bonds() || stage != 1) return;
+  PortalZoneArgs z = zone_args(*this, grid_, ctr_.p, pos_[cur_].p, id_[cur_].p, start_.p, pblk_.p, zone_entries_,
+                               zone_off(), zcnt_.p, zid_.p, slot_of_id_.p, id_cap_);
+  begin_timed(5);
+  launch_zone_mark(z, 1, stream_);
+  end_timed();
+}
+
 void Engine::phase_unmark_halo() {
+  if (has_zones() && has_bonds() && cap_ != 0) {
+    PortalZoneArgs z = zone_args(*this, grid_, ctr_.p, pos_[cur_].p, id_[cur_].p, start_.p, pblk_.p, zone_entries_,
+                                 zone_off(), zcnt_.p, zid_.p, slot_of_id_.p, id_cap_);
+    begin_timed(5);
+    launch_zone_mark(z, 0, stream_);
+    end_timed();
+  }
   if (strip_.world == 1 || !has_bonds() || cap_ == 0) return;
   StripState& s = strip_;
   GhostUnmarkArgs g{};
@@ -284,6 +344,27 @@ struct LocalGroup : Transport {
   }
   void halo(Engine&, int) override {}
   void migrants(Engine&) override {}
+  void zones(Engine&, int) override {}
+  void zones_all(int stage) {   // sum of the tables of all strips (each entry has one owner), given to everybody
+    if (!e[0]->has_zones()) return;
+    int *p0, *c0, *i0;
+    size_t np, nc, ni;
+    e[0]->zone_buffers(stage, &p0, &np, &c0, &nc, &i0, &ni);
+    for (size_t r = 1; r < e.size(); ++r) {
+      int *p, *c, *i;
+      e[r]->zone_buffers(stage, &p, &np, &c, &nc, &i, &ni);
+      launch_sum_i32(p0, p, np, stream);
+      launch_sum_i32(c0, c, nc, stream);
+      launch_sum_i32(i0, i, ni, stream);
+    }
+    for (size_t r = 1; r < e.size(); ++r) {
+      int *p, *c, *i;
+      e[r]->zone_buffers(stage, &p, &np, &c, &nc, &i, &ni);
+      copy(p, p0, np * sizeof(int));
+      copy(c, c0, nc * sizeof(int));
+      copy(i, i0, ni * sizeof(int));
+    }
+  }
 
   void step_n(int iters) {
     for (int it = 0; it < iters; ++it) {
@@ -291,10 +372,15 @@ struct LocalGroup : Transport {
       for (auto* x : e) x->phase_pack_halo(1);
       halo_all(1);
       for (auto* x : e) x->phase_install_halo(1);
+      for (auto* x : e) x->phase_pack_zones(1);
+      zones_all(1);
+      for (auto* x : e) x->phase_mark_zones(1);
       for (auto* x : e) x->phase_stage1();
       for (auto* x : e) x->phase_pack_halo(2);
       halo_all(2);
       for (auto* x : e) x->phase_install_halo(2);
+      for (auto* x : e) x->phase_pack_zones(2);
+      zones_all(2);
       for (auto* x : e) x->phase_stage2();
       for (auto* x : e) x->phase_unmark_halo();
       migrants_all();
@@ -352,6 +438,18 @@ struct NcclTransport : Transport {
         }
       }
     }
+    NCCL_CHECK(NcclApi::get().GroupEnd());
+  }
+  void zones(Engine& e, int stage) override {
+    // every entry of the zone table is written by exactly one strip (the owner of the block) and
+    // zero elsewhere, so the integer sum over the strips is that strip's value, bit for bit
+    int *p, *c, *i;
+    size_t np, nc, ni;
+    e.zone_buffers(stage, &p, &np, &c, &nc, &i, &ni);
+    NCCL_CHECK(NcclApi::get().GroupStart());
+    NCCL_CHECK(NcclApi::get().AllReduce(p, p, np, ncclInt32, ncclSum, comm, e.stream()));
+    NCCL_CHECK(NcclApi::get().AllReduce(c, c, nc, ncclInt32, ncclSum, comm, e.stream()));
+    NCCL_CHECK(NcclApi::get().AllReduce(i, i, ni, ncclInt32, ncclSum, comm, e.stream()));
     NCCL_CHECK(NcclApi::get().GroupEnd());
   }
   void migrants(Engine& e) override {

@@ -230,15 +230,18 @@ void Engine::alloc_cells() {
 void Engine::ensure_capacity(size_t n) {
   // strips: the ghost rows live right before slot 0 and right behind the last owned particle
   const size_t gh = strip_.world > 1 ? (size_t)strip_.ghost_cap : 0;
-  if (n <= cap_ && pos_[0].head >= gh && pos_h_.head >= gh) return;
+  const size_t zone = strip_.world > 1 ? (size_t)zone_entries_ * kZoneCap : 0;   // portal zone table behind the ghosts
+  if (n <= cap_ && pos_[0].head >= gh && pos_h_.head >= gh && pos_[0].n >= cap_ + gh + zone &&
+      pos_[1].n >= cap_ + gh + zone && pos_h_.n >= cap_ + gh + zone)
+    return;
   size_t nc = n <= cap_ ? cap_ : std::max<size_t>(n, cap_ + cap_ / 2);
   nc = (nc + 1023) / 1024 * 1024;
   for (int k = 0; k < 2; ++k) {
-    pos_[k].grow_keep(nc + gh, stream_, gh);
+    pos_[k].grow_keep(nc + gh + zone, stream_, gh);
     vel_[k].grow_keep(nc, stream_);
     id_[k].grow_keep(nc, stream_);
   }
-  pos_h_.alloc(nc + gh, gh);
+  pos_h_.alloc(nc + gh + zone, gh);
   vel_h_.alloc(nc);
   newcell_.alloc(nc);
   bslot_.alloc(nc * 8);
@@ -486,6 +489,31 @@ void Engine::sync_env() {
         }
       }
     }
+    if (strip_.world > 1) {
+      // Strips: the portal-zone table also serves bond partners on the far side of a
+      // portal.  Those need not lie in Portal::blocks, so the table is extended - behind the
+      // regular entries, which keep their indices - by the blocks within bond reach of a portal.
+      const float R = (float)((double)vlen(bs_) * 0.5);
+      const double reach_b = 0.25;
+      for (auto& pr : portals_)
+        for (const PortalHost* p : {&pr.first, &pr.second}) {
+          if (!(p->begin.x == p->begin.x && p->end.x == p->end.x)) continue;
+          auto clampi = [](double v, int lo, int hi) { return (int)std::max<double>(lo, std::min<double>(hi, v)); };
+          const double pad = reach_b + 2.0 * bs_.x;
+          const int i0 = clampi(std::floor((std::min(p->begin.x, p->end.x) - pad - gA_.x) / bs_.x), 0, di_ - 1);
+          const int i1 = clampi(std::floor((std::max(p->begin.x, p->end.x) + pad - gA_.x) / bs_.x), 0, di_ - 1);
+          const int j0 = clampi(std::floor((std::min(p->begin.y, p->end.y) - pad - gA_.y) / bs_.y), 0, dj_ - 1);
+          const int j1 = clampi(std::floor((std::max(p->begin.y, p->end.y) + pad - gA_.y) / bs_.y), 0, dj_ - 1);
+          for (int mi = i0; mi <= i1; ++mi)
+            for (int mj = j0; mj <= j1; ++mj) {
+              const V2 c = vadd(gA_, V2{(float)((0.5 + mi) * (double)bs_.x), (float)((0.5 + mj) * (double)bs_.y)});
+              const int b = mi * dj_ + mj;
+              if (vdist(seg_nearest(p->begin, p->end, c), c) < R + reach_b &&
+                  !std::binary_search(p->blocks.begin(), p->blocks.end(), b))
+                blk.push_back(b);
+            }
+        }
+    }
     sides_.alloc(sides.size());
     pblk_ptr_.alloc(ptr.size());
     pblk_.alloc(blk.size() + 1);
@@ -496,6 +524,14 @@ void Engine::sync_env() {
       CUDA_CHECK(cudaMemcpy(pblk_.p, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice));
     blk_flags_.alloc(nblk);
     CUDA_CHECK(cudaMemcpy(blk_flags_.p, flags.data(), nblk, cudaMemcpyHostToDevice));
+    zone_entries_ = (int)blk.size();
+    if (strip_.world > 1) {   // room for the portal zone table
+      zcnt_.alloc(blk.size() + 1);
+      zid_.alloc(blk.size() * kZoneCap + 1);
+      ensure_capacity(cap_);
+    }
+  } else {
+    zone_entries_ = 0;
   }
   env_dirty_ = false;
 }
@@ -772,6 +808,8 @@ StageArgs Engine::make_stage_args(int stage) {
   a.n_sides = has_portal_tables_ ? (int)portals_.size() * 2 : 0;
   a.sides = sides_.p; a.pblk_ptr = pblk_ptr_.p; a.pblk = pblk_.p;
   a.blk_flags = has_portal_tables_ ? blk_flags_.p : nullptr;
+  a.zcnt = has_zones() ? zcnt_.p : nullptr;
+  a.zoff = (int)zone_off();
   a.need_id = a.has_frozen || a.has_bonds || pick_enabled_ || strip_.world > 1;
   a.force_out = nullptr;
   a.newcell = newcell_.p; a.cnt = cnt_.p;
@@ -966,9 +1004,15 @@ void Engine::phase_end() {
 
 void Engine::iterate() {
   phase_prepare();
-  if (transport_) { phase_pack_halo(1); transport_->halo(*this, 1); phase_install_halo(1); }
+  if (transport_) {
+    phase_pack_halo(1); transport_->halo(*this, 1); phase_install_halo(1);
+    if (has_zones()) { phase_pack_zones(1); transport_->zones(*this, 1); phase_mark_zones(1); }
+  }
   phase_stage1();
-  if (transport_) { phase_pack_halo(2); transport_->halo(*this, 2); phase_install_halo(2); }
+  if (transport_) {
+    phase_pack_halo(2); transport_->halo(*this, 2); phase_install_halo(2);
+    if (has_zones()) { phase_pack_zones(2); transport_->zones(*this, 2); }
+  }
   phase_stage2();
   if (transport_) { phase_unmark_halo(); transport_->migrants(*this); }
   phase_reorder();

@@ -127,6 +127,11 @@ class Engine {
   void phase_pack_halo(int stage);   // boundary rows -> send buffers (stage 1: x0 + start slice, 2: x_half)
   void phase_install_halo(int stage);  // received boundary rows -> ghost rows (positions, start[], id -> slot map)
   void phase_unmark_halo();    // ghosts leave the id -> slot map again (before the reorder)
+  void phase_pack_zones(int stage);    // portal-zone particles of the blocks this strip owns -> zone table
+  void phase_mark_zones(int stage);    // after the tables were summed over the strips
+  bool has_zones() const { return strip_.world > 1 && has_portal_tables_ && zone_entries_ > 0; }
+  // the three arrays of the zone table for `stage` (device pointers, as int32 counts) for the transports
+  void zone_buffers(int stage, int** pos_i32, size_t* n_pos, int** cnt, size_t* n_cnt, int** ids, size_t* n_ids);
   void phase_stage1();
   bool has_bonds() const { return !bonds_.empty() || (strip_.world > 1 && strip_.bonds); }
   bool has_portals() const { return !portals_.empty(); }
@@ -213,6 +218,9 @@ class Engine {
   DevBuf<int> bond_col_;
   DevBuf<PortalSide> sides_;
   DevBuf<int> pblk_ptr_, pblk_;
+  DevBuf<int> zcnt_, zid_;        // portal zone table (strips): particles per listed block, their ids
+  int zone_entries_ = 0;          // listed portal blocks (pblk_ptr[n_sides])
+  size_t zone_off() const { return cap_ + (size_t)strip_.ghost_cap; }   // slot of the table's first particle
   DevBuf<uint8_t> blk_flags_;
   bool has_portal_tables_ = false;
   GridDev grid_{};
@@ -281,6 +289,7 @@ struct Transport {
   virtual ~Transport() {}
   virtual void halo(Engine& e, int stage) = 0;
   virtual void migrants(Engine& e) = 0;
+  virtual void zones(Engine& e, int stage) = 0;   // sum the portal zone tables over the strips
 };
 
 void set_last_error(const std::string& m);

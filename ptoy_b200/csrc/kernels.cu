@@ -353,6 +353,46 @@ __global__ void __launch_bounds__(kThreads) ghost_unmark_kernel(const __grid_con
   if (sl != kSlotNone && (sl < 0 || sl >= a.ctr->n_cur)) a.slot_of_id[pid] = kSlotNone;
 }
 
+// One thread per listed portal block: the particles of a block this strip owns go into the
+// zone table in (sub-row, slot) order; entries of other strips' blocks stay zero (the tables are
+// summed over the strips afterwards).
+__global__ void __launch_bounds__(kThreads) zone_pack_kernel(const __grid_constant__ PortalZoneArgs a) {
+  const int l = blockIdx.x * kThreads + threadIdx.x;
+  if (l >= a.n_entries) return;
+  int r0, r1, c0, c1;
+  block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
+  float2* out = a.X + a.zoff + (size_t)l * kZoneCap;
+  int* oid = a.zid + (size_t)l * kZoneCap;
+  int k = 0;
+  for (int Rg = r0; Rg <= r1; ++Rg) {
+    const int R = Rg - a.g.row0;
+    if (R < a.g.own_lo || R >= a.g.own_hi) continue;
+    const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
+    for (int q = beg; q < end; ++q, ++k)
+      if (k < kZoneCap) { out[k] = a.X_in[q]; oid[k] = a.id[q]; }
+  }
+  if (k > kZoneCap) { atomicOr(a.err, 128); k = kZoneCap; }
+  a.zcnt[l] = k;
+}
+
+// mark = 1: zone particles that are neither local nor ghosts enter the id -> slot map (a bond
+// partner on the far side of a portal, on another strip); mark = 0: they leave it again.
+__global__ void __launch_bounds__(kThreads) zone_mark_kernel(const __grid_constant__ PortalZoneArgs a, int mark) {
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  const int l = t / kZoneCap, k = t - l * kZoneCap;
+  if (l >= a.n_entries || k >= a.zcnt[l]) return;
+  const int pid = a.zid[t];
+  if (pid < 0 || pid >= a.id_cap) return;
+  const int slot = a.zoff + t;
+  if (mark) { if (a.slot_of_id[pid] == kSlotNone) a.slot_of_id[pid] = slot; }
+  else if (a.slot_of_id[pid] >= a.zoff) a.slot_of_id[pid] = kSlotNone;
+}
+
+__global__ void sum_i32_kernel(int* dst, const int* src, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
 // ---------------------------------------------------------------------------------
 // read-back helpers
 // ---------------------------------------------------------------------------------
@@ -457,6 +497,15 @@ void launch_ghost_install(const GhostInstallArgs& a, cudaStream_t s) {
 }
 void launch_ghost_unmark(const GhostUnmarkArgs& a, cudaStream_t s) {
   ghost_unmark_kernel<<<dim3(grid_for((size_t)a.ghost_cap), 2), kThreads, 0, s>>>(a);
+}
+void launch_zone_pack(const PortalZoneArgs& a, cudaStream_t s) {
+  if (a.n_entries > 0) zone_pack_kernel<<<grid_for((size_t)a.n_entries), kThreads, 0, s>>>(a);
+}
+void launch_zone_mark(const PortalZoneArgs& a, int mark, cudaStream_t s) {
+  if (a.n_entries > 0) zone_mark_kernel<<<grid_for((size_t)a.n_entries * kZoneCap), kThreads, 0, s>>>(a, mark);
+}
+void launch_sum_i32(int* dst, const int* src, size_t n, cudaStream_t s) {
+  if (n) sum_i32_kernel<<<grid_for(n), kThreads, 0, s>>>(dst, src, n);
 }
 void launch_arrivals(const ArrivalArgs& a, cudaStream_t s) {
   arrivals_kernel<<<grid_for((size_t)a.world * a.in_cap), kThreads, 0, s>>>(a);

@@ -274,7 +274,25 @@ __device__ __forceinline__ void force_one_bond(const StageArgs& a, float2 x, int
   fy = fadd(fy, by);
 }
 
-// cross-portal forces (particles.cpp:318-381) for a particle in reference block `blk`
+// cross-portal forces (particles.cpp:318-381) for a particle in reference block `blk`.
+// The particles of a listed block are read in place (one strip) or from the gathered zone table
+// (strips: PortalZoneArgs) - in both cases in the order sub-row, slot.
+template <class F>
+__device__ __forceinline__ void for_block_particles(const StageArgs& a, const float2* __restrict__ X, int l, F&& f) {
+  if (a.zcnt) {
+    const int n = a.zcnt[l];
+    const float2* P = X + a.zoff + (size_t)l * kZoneCap;
+    for (int k = 0; k < n; ++k) f(P[k]);
+  } else {
+    int r0, r1, c0, c1;
+    block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
+    for (int R = r0; R <= r1; ++R) {
+      const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
+      for (int q = beg; q < end; ++q) f(X[q]);
+    }
+  }
+}
+
 __device__ __forceinline__ void force_portal_cross(const StageArgs& a, const float2* __restrict__ X, float2 x, int blk, float& fx, float& fy) {
   const Phys& ph = a.ph;
   for (int s = 0; s < a.n_sides; ++s) {
@@ -286,56 +304,40 @@ __device__ __forceinline__ void force_portal_cross(const StageArgs& a, const flo
     portal_coords(po, x.x, x.y, lambda_c, offset_c);
     if (!(lambda_c > 0.0f && lambda_c < 1.0f)) continue;
     for (int l = lb; l < le; ++l) {                                          // :345-355
-      int r0, r1, c0, c1;
-      block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
-      for (int Rg = r0; Rg <= r1; ++Rg) {
-        const int R = Rg - a.g.row0;
-        if (R < 0 || R >= a.g.SI) continue;   // strips: rows this rank does not store
-        const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
-        for (int q = beg; q < end; ++q) {
-          const float2 nb = X[q];
-          float ln, on;
-          portal_coords(po, nb.x, nb.y, ln, on);
-          if (ln > 0.0f && ln < 1.0f && fmul(on, offset_c) < 0.0f) {
-            const float dx = fsub(x.x, nb.x), dy = fsub(x.y, nb.y);
-            const float r2 = dot2(dx, dy, dx, dy);
-            if (r2 < ph.r2c) {
-              float px, py;
-              pair_force(ph, dx, dy, r2, px, py);
-              fx = fsub(fx, px);
-              fy = fsub(fy, py);
-            }
+      for_block_particles(a, X, l, [&](float2 nb) {
+        float ln, on;
+        portal_coords(po, nb.x, nb.y, ln, on);
+        if (ln > 0.0f && ln < 1.0f && fmul(on, offset_c) < 0.0f) {
+          const float dx = fsub(x.x, nb.x), dy = fsub(x.y, nb.y);
+          const float r2 = dot2(dx, dy, dx, dy);
+          if (r2 < ph.r2c) {
+            float px, py;
+            pair_force(ph, dx, dy, r2, px, py);
+            fx = fsub(fx, px);
+            fy = fsub(fy, py);
           }
         }
-      }
+      });
     }
     const int ob = a.pblk_ptr[s ^ 1], oe = a.pblk_ptr[(s ^ 1) + 1];               // :358-375
     const float sign = (offset_c > 0.0f) ? 1.0f : -1.0f;
     for (int l = ob; l < oe; ++l) {
-      int r0, r1, c0, c1;
-      block_extent(a.g, a.pblk[l], r0, r1, c0, c1);
-      for (int Rg = r0; Rg <= r1; ++Rg) {
-        const int R = Rg - a.g.row0;
-        if (R < 0 || R >= a.g.SI) continue;
-        const int beg = a.start[R * a.g.SJ + c0], end = a.start[R * a.g.SJ + c1 + 1];
-        for (int q = beg; q < end; ++q) {
-          const float2 nb = X[q];
-          float oln, oon;
-          portal_coords(ot, nb.x, nb.y, oln, oon);
-          if (oln > 0.0f && oln < 1.0f && fmul(oon, offset_c) < 0.0f) {
-            float jx, jy;
-            portal_image(ph, po, oln, oon, sign, jx, jy);
-            const float dx = fsub(x.x, jx), dy = fsub(x.y, jy);
-            const float r2 = dot2(dx, dy, dx, dy);
-            if (r2 < ph.r2c) {
-              float px, py;
-              pair_force(ph, dx, dy, r2, px, py);
-              fx = fadd(fx, px);
-              fy = fadd(fy, py);
-            }
+      for_block_particles(a, X, l, [&](float2 nb) {
+        float oln, oon;
+        portal_coords(ot, nb.x, nb.y, oln, oon);
+        if (oln > 0.0f && oln < 1.0f && fmul(oon, offset_c) < 0.0f) {
+          float jx, jy;
+          portal_image(ph, po, oln, oon, sign, jx, jy);
+          const float dx = fsub(x.x, jx), dy = fsub(x.y, jy);
+          const float r2 = dot2(dx, dy, dx, dy);
+          if (r2 < ph.r2c) {
+            float px, py;
+            pair_force(ph, dx, dy, r2, px, py);
+            fx = fadd(fx, px);
+            fy = fadd(fy, py);
           }
         }
-      }
+      });
     }
   }
 }

@@ -158,3 +158,63 @@ def test_bond_rows_travel_with_their_particle(world, ghost_rows):
     assert moved > 50, moved             # bonded particles did change strips
     assert n_got == n_ref == sc.n
     assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])
+
+
+def _portal_scene(n=30000, pairs=6, seed=41, bonds=False):
+    """configs[3] in small: dense packing with random velocities and vertical portal pairs INSIDE
+    the packing, placed so that some portals straddle strip boundaries and the two portals of a
+    pair lie on different strips (cross-portal forces and teleports then need the other strips)."""
+    sc = scenes.hex_lattice(n, 2.2 if not bonds else 2.02, 0.025 if not bonds else 0.01, seed=seed, vel_scale=3.0)
+    ax, ay, bx, by = sc.domain
+    w, h = bx - ax, by - ay
+    rng = np.random.RandomState(seed)
+    sc.portals = []
+    for p in range(pairs):
+        x0 = ax + w * (0.08 + 0.38 * rng.uniform())
+        x1 = ax + w * (0.55 + 0.38 * rng.uniform())
+        y0 = ay + 0.1 + (h - 0.7) * rng.uniform()
+        y1 = ay + 0.1 + (h - 0.7) * rng.uniform()
+        sc.portals.append(((x0, y0), (x0, y0 + 0.5), (x1, y1), (x1, y1 + 0.5)))
+    if bonds:
+        scenes.add_lattice_bonds(sc)
+    return sc
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_portal_pairs_across_strips(world):
+    """Cross-portal pair forces (particles.cpp:318-381) and teleports when a portal's partner - or
+    part of its own block list - lives on another strip: the portal-zone table gathered over the
+    strips reproduces the single engine bit for bit."""
+    sc = _portal_scene()
+
+    def setup(p):
+        for q in sc.portals:
+            p.add_portal_pair(*q)
+    ref, n_ref = single(sc, 50, setup)
+    got, n_got = strips(sc, 50, world, setup=setup)
+    assert n_got == n_ref
+    teleported = np.abs(ref["pos"][:, 0] - sc.pos[:, 0]) > 1.0
+    assert teleported.sum() > 20, teleported.sum()
+    assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])
+    assert np.array_equal(got["block"], ref["block"])
+
+
+def test_bonds_through_portals_across_strips():
+    """A bonded sheet with portal pairs: bonds whose partner went through a portal to another
+    strip (particles.cpp:784-819) find it in the portal-zone table.  (Particles inside a portal
+    slab teleport in the first iteration; the run is short enough for the pairs to stay inside
+    the portal zones - a partner that is neither in a ghost row nor in a portal zone is the
+    documented limit of the decomposition and raises error bit 16.)"""
+    sc = _portal_scene(n=20000, pairs=4, seed=43, bonds=True)
+    sc.vel *= np.float32(0.3)
+
+    def setup(p):
+        for q in sc.portals:
+            p.add_portal_pair(*q)
+        p.set_bonds(sc.bonds)
+    ref, n_ref = single(sc, 12, setup)
+    got, n_got = strips(sc, 12, 4, setup=setup, bonds=True, ghost_rows=6)
+    assert n_got == n_ref
+    teleported = np.abs(ref["pos"][:, 0] - sc.pos[:, 0]) > 1.0
+    assert teleported.sum() > 10, teleported.sum()
+    assert bits_equal(got["pos"], ref["pos"]) and bits_equal(got["vel"], ref["vel"])

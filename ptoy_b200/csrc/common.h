@@ -116,6 +116,7 @@ struct Counters {
   int err_flags;
   int n_fix;        // cells filed for fixup_kernel by the current reorder
   unsigned dmax;    // float bits: largest per-component half-step drift measured by stage 1
+  int lost[4];      // first bond whose partner could not be served (error bit 16): id, partner id, slot, n_cur
 };
 
 struct StageArgs {
@@ -153,6 +154,7 @@ struct StageArgs {
   int cap;                     // stride of the slot-major bslot array
   int id_cap;                  // entries of the id-indexed tables (slot_of_id, bond_ell, frozen_bits)
   int* err;                    // sticky error bits (Counters::err_flags)
+  int* lost;                   // Counters::lost
   // portals
   int n_sides;           // 2 * pairs
   const PortalSide* sides;

@@ -111,17 +111,21 @@ void Engine::alloc_strip_buffers() {
   s.ghost_cap = std::max(4096, s.ghost_rows * grid_.SJ * 8);
   s.out_cap = 1 << 14;
   if (const char* v = std::getenv("PTOY_MIGRANT_CAP")) s.out_cap = std::max(256, atoi(v));
-  const size_t nstart = (size_t)s.ghost_rows * grid_.SJ + 1;
+  s.nstart = (size_t)s.ghost_rows * grid_.SJ + 1;
+  auto up16 = [](size_t b) { return (b + 15) / 16 * 16; };
+  s.halo_pos_bytes = up16((size_t)(s.ghost_cap + 2) * sizeof(float2));
+  const size_t start_bytes = up16(s.nstart * sizeof(int));
+  s.halo_bytes = s.halo_pos_bytes + start_bytes + up16((size_t)s.ghost_cap * sizeof(int));
   for (int sd = 0; sd < 2; ++sd) {
-    s.send_pos[sd].alloc(s.ghost_cap + 2);
-    s.send_start[sd].alloc(nstart);
-    s.ghost_pos[sd].alloc(s.ghost_cap + 2);
-    s.ghost_start[sd].alloc(nstart);
-    CUDA_CHECK(cudaMemsetAsync(s.ghost_pos[sd].p, 0, (s.ghost_cap + 2) * sizeof(float2), stream_));
-    CUDA_CHECK(cudaMemsetAsync(s.ghost_start[sd].p, 0, nstart * sizeof(int), stream_));
-    CUDA_CHECK(cudaMemsetAsync(s.send_start[sd].p, 0, nstart * sizeof(int), stream_));
-    s.send_id[sd].alloc(s.ghost_cap);
-    s.ghost_id[sd].alloc(s.ghost_cap);
+    s.send_raw[sd].alloc(s.halo_bytes);
+    s.recv_raw[sd].alloc(s.halo_bytes);
+    CUDA_CHECK(cudaMemsetAsync(s.send_raw[sd].p, 0, s.halo_bytes, stream_));
+    CUDA_CHECK(cudaMemsetAsync(s.recv_raw[sd].p, 0, s.halo_bytes, stream_));
+    for (auto pr : {std::make_pair(&s.send[sd], s.send_raw[sd].p), std::make_pair(&s.ghost[sd], s.recv_raw[sd].p)}) {
+      pr.first->pos = reinterpret_cast<float2*>(pr.second);
+      pr.first->start = reinterpret_cast<int*>(pr.second + s.halo_pos_bytes);
+      pr.first->id = reinterpret_cast<int*>(pr.second + s.halo_pos_bytes + start_bytes);
+    }
   }
   s.ghost_n.alloc(2);
   CUDA_CHECK(cudaMemsetAsync(s.ghost_n.p, 0, 2 * sizeof(int), stream_));
@@ -168,9 +172,9 @@ void Engine::phase_pack_halo(int stage) {
   g.row_lo[1] = grid_.own_hi - strip_.ghost_rows;
   g.ghost_cap = strip_.ghost_cap;
   for (int sd = 0; sd < 2; ++sd) {
-    g.out_pos[sd] = strip_.send_pos[sd].p;
-    g.out_start[sd] = stage == 1 ? strip_.send_start[sd].p : nullptr;
-    g.out_id[sd] = (stage == 1 && has_bonds()) ? strip_.send_id[sd].p : nullptr;
+    g.out_pos[sd] = strip_.send[sd].pos;
+    g.out_start[sd] = stage == 1 ? strip_.send[sd].start : nullptr;
+    g.out_id[sd] = (stage == 1 && has_bonds()) ? strip_.send[sd].id : nullptr;
   }
   g.id = id_[cur_].p;
   g.dmax = stage == 2 ? &ctr_.p->dmax : nullptr;
@@ -196,9 +200,9 @@ void Engine::phase_install_halo(int stage) {
   g.ghost_cap = s.ghost_cap;
   for (int sd = 0; sd < 2; ++sd) {
     const bool have = sd == 0 ? s.rank > 0 : s.rank + 1 < s.world;
-    g.in_pos[sd] = have ? s.ghost_pos[sd].p : nullptr;
-    g.in_start[sd] = s.ghost_start[sd].p;
-    g.in_id[sd] = (have && has_bonds()) ? s.ghost_id[sd].p : nullptr;
+    g.in_pos[sd] = have ? s.ghost[sd].pos : nullptr;
+    g.in_start[sd] = s.ghost[sd].start;
+    g.in_id[sd] = (have && has_bonds()) ? s.ghost[sd].id : nullptr;
     g.count[sd] = s.ghost_n.p + sd;
   }
   g.X = stage == 1 ? pos_[cur_].p : pos_h_.p;
@@ -279,7 +283,7 @@ void Engine::phase_unmark_halo() {
   g.ghost_cap = s.ghost_cap;
   for (int sd = 0; sd < 2; ++sd) {
     const bool have = sd == 0 ? s.rank > 0 : s.rank + 1 < s.world;
-    g.in_id[sd] = have ? s.ghost_id[sd].p : nullptr;
+    g.in_id[sd] = have ? s.ghost[sd].id : nullptr;
     g.count[sd] = s.ghost_n.p + sd;
   }
   begin_timed(5);
@@ -317,20 +321,9 @@ struct LocalGroup : Transport {
     const int n = (int)e.size();
     for (int r = 0; r < n; ++r) {
       StripState& me = e[r]->strip_mut();
-      const size_t pb = (size_t)(me.ghost_cap + 2) * sizeof(float2), sb = me.send_start[0].n * sizeof(int);
-      const size_t ib = (size_t)me.ghost_cap * sizeof(int);
-      if (r > 0) {  // my first rows -> left neighbour's right ghost
-        StripState& l = e[r - 1]->strip_mut();
-        copy(l.ghost_pos[1].p, me.send_pos[0].p, pb);
-        if (stage == 1) copy(l.ghost_start[1].p, me.send_start[0].p, sb);
-        if (stage == 1 && e[r]->has_bonds()) copy(l.ghost_id[1].p, me.send_id[0].p, ib);
-      }
-      if (r + 1 < n) {  // my last rows -> right neighbour's left ghost
-        StripState& rr = e[r + 1]->strip_mut();
-        copy(rr.ghost_pos[0].p, me.send_pos[1].p, pb);
-        if (stage == 1) copy(rr.ghost_start[0].p, me.send_start[1].p, sb);
-        if (stage == 1 && e[r]->has_bonds()) copy(rr.ghost_id[0].p, me.send_id[1].p, ib);
-      }
+      const size_t bytes = stage == 1 ? me.halo_bytes : me.halo_pos_bytes;
+      if (r > 0) copy(e[r - 1]->strip_mut().recv_raw[1].p, me.send_raw[0].p, bytes);   // my first rows -> left neighbour's right ghost
+      if (r + 1 < n) copy(e[r + 1]->strip_mut().recv_raw[0].p, me.send_raw[1].p, bytes);   // my last rows -> right neighbour's left ghost
     }
   }
   void migrants_all() {
@@ -420,23 +413,15 @@ struct NcclTransport : Transport {
   }
   void halo(Engine& e, int stage) override {
     StripState& s = e.strip_mut();
-    const size_t pb = (size_t)(s.ghost_cap + 2) * sizeof(float2), sb = s.send_start[0].n * sizeof(int);
-    const size_t ib = (size_t)s.ghost_cap * sizeof(int);
+    // ONE message per neighbour: positions | start[] slice | ids (stage 2: the positions only)
+    const size_t bytes = stage == 1 ? s.halo_bytes : s.halo_pos_bytes;
     NCCL_CHECK(NcclApi::get().GroupStart());
     for (int sd = 0; sd < 2; ++sd) {
       const int peer = sd == 0 ? s.rank - 1 : s.rank + 1;
       if (peer < 0 || peer >= s.world) continue;
       // my boundary rows on side sd become the peer's ghost on its opposite side; symmetric recv
-      NCCL_CHECK(NcclApi::get().Send(s.send_pos[sd].p, pb, ncclChar, peer, comm, e.stream()));
-      NCCL_CHECK(NcclApi::get().Recv(s.ghost_pos[sd].p, pb, ncclChar, peer, comm, e.stream()));
-      if (stage == 1) {
-        NCCL_CHECK(NcclApi::get().Send(s.send_start[sd].p, sb, ncclChar, peer, comm, e.stream()));
-        NCCL_CHECK(NcclApi::get().Recv(s.ghost_start[sd].p, sb, ncclChar, peer, comm, e.stream()));
-        if (e.has_bonds()) {  // `bonds` was agreed at configure time, so both ends post the pair
-          NCCL_CHECK(NcclApi::get().Send(s.send_id[sd].p, ib, ncclChar, peer, comm, e.stream()));
-          NCCL_CHECK(NcclApi::get().Recv(s.ghost_id[sd].p, ib, ncclChar, peer, comm, e.stream()));
-        }
-      }
+      NCCL_CHECK(NcclApi::get().Send(s.send_raw[sd].p, bytes, ncclChar, peer, comm, e.stream()));
+      NCCL_CHECK(NcclApi::get().Recv(s.recv_raw[sd].p, bytes, ncclChar, peer, comm, e.stream()));
     }
     NCCL_CHECK(NcclApi::get().GroupEnd());
   }

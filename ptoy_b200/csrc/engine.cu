@@ -805,6 +805,7 @@ StageArgs Engine::make_stage_args(int stage) {
   a.cap = (int)cap_;
   a.id_cap = (int)id_cap_;
   a.err = &ctr_.p->err_flags;
+  a.lost = ctr_.p->lost;
   a.n_sides = has_portal_tables_ ? (int)portals_.size() * 2 : 0;
   a.sides = sides_.p; a.pblk_ptr = pblk_ptr_.p; a.pblk = pblk_.p;
   a.blk_flags = has_portal_tables_ ? blk_flags_.p : nullptr;
@@ -1030,7 +1031,14 @@ void Engine::check_device_errors(bool wait) {
   const int f = *h_err_;
   if (!f) return;
   const int code = (f & (16 | 64)) ? -5 : -4;
-  throw Error(code, "device error flags " + std::to_string(f) +
+  std::string where;
+  if (f & 16) {
+    read_counters();
+    where = " [first lost bond: particle id " + std::to_string(h_ctr_->lost[0]) + " (slot " + std::to_string(h_ctr_->lost[2]) +
+            " of " + std::to_string(h_ctr_->lost[3]) + ") -> partner id " + std::to_string(h_ctr_->lost[1]) + ", rank " +
+            std::to_string(strip_.rank) + "]";
+  }
+  throw Error(code, "device error flags " + std::to_string(f) + where +
                         " (see ptoy_error_flags in include/ptoy_b200.h): the simulation state is no longer valid");
 }
 void Engine::step_to(float time_target) {

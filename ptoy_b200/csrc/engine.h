@@ -4,6 +4,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -48,11 +49,13 @@ struct StripState {
   int ghost_rows = 2;                  // boundary sub-rows mirrored on either side (>= 2; wider for long bonds)
   bool bonds = false;                  // the decomposed scene has bonds (agreed across ranks at configure time)
   int ghost_cap = 0, out_cap = 0;
-  DevBuf<float2> send_pos[2];          // my boundary rows for the left / right neighbour (+ drift in the last element)
-  DevBuf<int> send_start[2];
-  DevBuf<float2> ghost_pos[2];         // neighbours' boundary rows as received (x0, then x_half)
-  DevBuf<int> ghost_start[2];
-  DevBuf<int> send_id[2], ghost_id[2]; // ids of the boundary rows (bonds across strips)
+  // One message per neighbour and stage: positions (+ the sender's drift in the last element) |
+  // start[] slice | ids, contiguous in `send_raw` / `recv_raw`; stage 2 sends the positions only.
+  struct HaloView { float2* pos = nullptr; int* start = nullptr; int* id = nullptr; };
+  DevBuf<unsigned char> send_raw[2], recv_raw[2];
+  HaloView send[2], ghost[2];          // my boundary rows for the left / right neighbour; theirs as received
+  size_t halo_pos_bytes = 0, halo_bytes = 0;   // bytes of the positions part / of the whole message
+  size_t nstart = 0;
   DevBuf<int> ghost_n;                 // [2] ghosts installed per side this iteration
   DevBuf<unsigned char> outbox, inbox; // world blocks each (common.h DistDev layout)
   DevBuf<unsigned long long> arr_vkey;

@@ -508,7 +508,12 @@ stage_tile_kernel(const __grid_constant__ StageArgs a) {
             bool lost = false;
 #pragma unroll
             for (int k = 0; k < kBondPlan; ++k) lost |= bcol[k] >= 0 && bslot[k] == kSlotNone;
-            if (lost) atomicOr(a.err, 16);
+            if (lost && !(atomicOr(a.err, 16) & 16)) {   // the first one leaves a trace for the error message
+              int kk = 0;
+#pragma unroll
+              for (int k = kBondPlan - 1; k >= 0; --k) if (bcol[k] >= 0 && bslot[k] == kSlotNone) kk = k;
+              a.lost[0] = pid; a.lost[1] = bcol[kk]; a.lost[2] = i; a.lost[3] = n;
+            }
           }
           hand[0] = make_int4(bslot[0], bslot[1], bslot[2], bslot[3]);
           hand[1] = make_int4(bslot[4], bslot[5], kSlotNone, nb);

@@ -194,6 +194,20 @@ int ptoy_id_capacity(ptoy_engine* h, size_t* n);
 /* blocks::FindBlock (blocks.h:155-163) evaluated on the device for n points; -1 = none. */
 int ptoy_find_blocks(ptoy_engine* h, const float* pos_xy, size_t n, int64_t* block);
 
+/* ---- wire format of the remote (WASM / browser) front end ------------------------------------
+ *
+ * The exports of ptoy_wasm.cpp:130-198 hand the browser uint16 pixel coordinates,
+ *   data[0] = (1 + p.x) * width * 0.5,   data[1] = (1 - p.y) * height * 0.5,
+ * `max_size` = capacity of `data` in uint16 entries (ptoy_inc.js:9-27 uses 10 000); *n = entries
+ * written.  ptoy_wire_particles replaces GetParticles (:130-146): the positions are quantised and
+ * culled ON THE DEVICE from the live state, so 4 bytes per drawn particle cross PCIe; the order
+ * is the engine's, not block order (the consumer draws points).  ptoy_wire_scene replaces
+ * GetPortals (what = 1, 8 entries per pair, the pair being drawn included, :147-166),
+ * GetBonds (2, 4 entries per drawn bond, :167-182) and GetFrozen (3, :183-198), built from the
+ * host state and the last render snapshot in the order UpdateScene (:47-116) builds its lists. */
+int ptoy_wire_particles(ptoy_engine* h, uint16_t* data, int max_size, int width, int height, int* n);
+int ptoy_wire_scene(ptoy_engine* h, int what, uint16_t* data, int max_size, int width, int height, int* n);
+
 /* ---- strip decomposition across GPUs (new work: the reference is single-process) ---
  *
  * The domain is cut into strips over the slow block index (blocks.h:160: block = i*dims.j + j):

@@ -201,6 +201,12 @@ int ptoy_id_capacity(ptoy_engine* h, size_t* n) { PTOY_TRY(h, *n = E.id_capacity
 int ptoy_find_blocks(ptoy_engine* h, const float* pos, size_t n, int64_t* block) {
   PTOY_TRY(h, E.find_blocks(pos, n, block))
 }
+int ptoy_wire_particles(ptoy_engine* h, uint16_t* data, int max_size, int width, int height, int* n) {
+  PTOY_TRY(h, *n = E.wire_particles(data, max_size, width, height))
+}
+int ptoy_wire_scene(ptoy_engine* h, int what, uint16_t* data, int max_size, int width, int height, int* n) {
+  PTOY_TRY(h, *n = E.wire_scene(what, data, max_size, width, height))
+}
 // ---- strip decomposition -----------------------------------------------------------------
 
 int ptoy_configure_strips(ptoy_engine* h, int rank, int world, const int32_t* col_begin, int ghost_rows,

@@ -92,6 +92,19 @@ struct Phys {
   float pkx, pky;
 };
 
+// Pixel coordinates of the remote front end's wire format (ptoy_wasm.cpp:130-198):
+//   data[0] = (1 + p.x) * width * 0.5,  data[1] = (1 - p.y) * height * 0.5   -> uint16_t
+// float sum, float product with the int width, product with the DOUBLE 0.5 (exact), truncation.
+__host__ __device__ inline unsigned wire_pixel(float x, float y, int width, int height) {
+#ifdef __CUDA_ARCH__
+  const float fx = __fmul_rn(__fadd_rn(1.0f, x), (float)width), fy = __fmul_rn(__fsub_rn(1.0f, y), (float)height);
+#else
+  const float fx = (1.0f + x) * (float)width, fy = (1.0f - y) * (float)height;
+#endif
+  const unsigned qx = (unsigned)(int)((double)fx * 0.5) & 0xffffu, qy = (unsigned)(int)((double)fy * 0.5) & 0xffffu;
+  return qx | (qy << 16);   // little endian: data[0] = x, data[1] = y
+}
+
 struct WallDev {
   float ax, ay, bx, by;          // line A,B (particles.h:35)
   float lox, loy, hix, hiy;      // bbox grown by wall_reach: outside it the force is 0
@@ -306,6 +319,7 @@ struct PortalZoneArgs {
 void launch_zone_pack(const PortalZoneArgs& a, cudaStream_t s);
 void launch_zone_mark(const PortalZoneArgs& a, int mark, cudaStream_t s);
 void launch_sum_i32(int* dst, const int* src, size_t n, cudaStream_t s);
+void launch_wire(const Counters* ctr, const float2* pos, int n_max, int width, int height, unsigned* out, cudaStream_t s);
 void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s);
 void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s);
 void launch_scan(int* cnt, int* start, int n_items, int ncell, unsigned long long* tile_state,

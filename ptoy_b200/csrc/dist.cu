@@ -110,7 +110,7 @@ void Engine::alloc_strip_buffers() {
   // the boundary sub-rows hold about ghost_rows*SJ*1.2 particles at dense packing; allow 8 per sub-cell
   s.ghost_cap = std::max(4096, s.ghost_rows * grid_.SJ * 8);
   s.out_cap = 1 << 14;
-  if (const char* v = std::getenv("PTOY_MIGRANT_CAP")) s.out_cap = std::max(256, atoi(v));
+  if (const char* v = std::getenv("PTOY_MIGRANT_CAP")) s.out_cap = std::max(16, atoi(v));
   s.nstart = (size_t)s.ghost_rows * grid_.SJ + 1;
   auto up16 = [](size_t b) { return (b + 15) / 16 * 16; };
   s.halo_pos_bytes = up16((size_t)(s.ghost_cap + 2) * sizeof(float2));

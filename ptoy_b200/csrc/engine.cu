@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1059,8 +1060,11 @@ void Engine::step_n(int n) {
 }
 void Engine::synchronize() {
   CUDA_CHECK(cudaSetDevice(device_));
+  // (a fresh copy of the flags: iterations driven by a strip group do not pass through step_n)
+  CUDA_CHECK(cudaMemcpyAsync(h_err_, &ctr_.p->err_flags, sizeof(int), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   CUDA_CHECK(cudaGetLastError());
+  err_pending_ = false;
   check_device_errors(true);
 }
 
@@ -1094,12 +1098,14 @@ void Engine::take_snapshot() {
   size_t mx = 0;
   for (size_t b = 0; b < nblk; ++b) { mx = std::max(mx, off[b + 1]); off[b + 1] += off[b]; }
   snap_pos_.resize(n); snap_vel_.resize(n); snap_id_.resize(n); snap_block_.resize(n);
+  snap_block_start_.assign(off.begin(), off.end());   // block b holds snapshot entries [start[b], start[b+1])
   for (size_t i = 0; i < n; ++i) {
     const size_t d = off[(size_t)blk[i]]++;
     snap_pos_[d] = p[i]; snap_vel_[d] = v[i]; snap_id_[d] = ids[i]; snap_block_[d] = blk[i];
   }
   snap_num_particles_ = n;
   snap_num_per_cell_ = mx;
+  snap_di_ = di_; snap_dj_ = dj_; snap_gA_ = gA_;
 }
 
 size_t Engine::snapshot(float* pos, float* vel, int32_t* id, int64_t* block, size_t cap) {
@@ -1214,6 +1220,72 @@ void Engine::find_blocks(const float* pos, size_t n, int64_t* block) {
   cudaFree(db);
 }
 
+// ---- wire format for remote front ends (ptoy_wasm.cpp:130-198) ---------------------------------
+// GetParticles: quantised on the device from the live state, culled to max_size entries; only the
+// 4 bytes per particle cross PCIe instead of 24.  (Engine order, not block order: the consumer
+// draws points, ptoy_inc.js:69-126; the cap of 10 000 entries keeps whichever come first.)
+int Engine::wire_particles(uint16_t* data, int max_size, int width, int height) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  if (max_size < 2 || !data) return 0;
+  read_counters();
+  const int n = std::min(h_ctr_->n_cur, max_size / 2);
+  if (n <= 0) return 0;
+  wire_.alloc((size_t)n);
+  launch_wire(ctr_.p, pos_[cur_].p, n, width, height, wire_.p, stream_);
+  ++launches_;
+  CUDA_CHECK(cudaMemcpyAsync(data, wire_.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  return 2 * n;
+}
+
+// GetPortals / GetBonds / GetFrozen (:147-198) from the host state and the render snapshot, in the
+// order UpdateScene (:47-116) builds the lists.
+int Engine::wire_scene(int what, uint16_t* data, int max_size, int width, int height) {
+  int i = 0;
+  auto append = [&](V2 p) {
+    const unsigned q = wire_pixel(p.x, p.y, width, height);
+    data[i] = (uint16_t)(q & 0xffffu); data[i + 1] = (uint16_t)(q >> 16);
+    i += 2;
+  };
+  if (what == 1) {          // portals, then the pair being drawn (:61-88)
+    std::vector<std::array<V2, 4>> list;
+    for (auto& pr : portals_) list.push_back({pr.first.begin, pr.first.end, pr.second.begin, pr.second.end});
+    const V2 none{-1.f, -1.f};
+    if (portal_stage_ == 0) {
+      if (portal_mouse_moving_) list.push_back({portal_begin_, portal_current_, none, none});
+    } else {
+      list.push_back({portal_prev_first_, portal_prev_second_, none, none});
+      if (portal_mouse_moving_) { list.back()[2] = portal_begin_; list.back()[3] = portal_current_; }
+    }
+    for (auto& q : list) {
+      if (i + 8 > max_size) break;
+      for (const V2& p : q) append(p);
+    }
+    return i;
+  }
+  std::vector<int> where(id_cap_ + 1, -1);
+  for (size_t k = 0; k < snap_id_.size(); ++k) where[snap_id_[k]] = (int)k;
+  if (what == 2) {          // bonds that are drawn (:90-104)
+    for (auto& b : bonds()) {
+      if (i + 4 > max_size) break;
+      if (std::binary_search(norend_buf_.begin(), norend_buf_.end(), b)) continue;
+      const int ia = where[b.first], ib = where[b.second];
+      if (ia < 0 || ib < 0) continue;
+      append(snap_pos_[ia]); append(snap_pos_[ib]);
+    }
+    return i;
+  }
+  if (what == 3) {          // frozen particles (:106-115)
+    for (int id : frozen_) {
+      if (i + 2 > max_size) break;
+      if ((size_t)id > id_cap_ || where[id] < 0) continue;
+      append(snap_pos_[where[id]]);
+    }
+    return i;
+  }
+  throw Error(-2, "wire_scene: what must be 1 (portals), 2 (bonds) or 3 (frozen)");
+}
+
 // ---- the constructor's scene (particles.cpp:34-76) ---------------------------------------------
 void Engine::load_default_scene() {
   reset_scene(V2{-1.f, -1.f}, V2{1.f, 1.f});
@@ -1248,35 +1320,73 @@ void Engine::portal_tool_state(int* sm, float* xy) const {
   xy[4] = portal_prev_first_.x; xy[5] = portal_prev_first_.y; xy[6] = portal_prev_second_.x; xy[7] = portal_prev_second_.y;
 }
 
+// The UI tools look particles up by position (particles.cpp:228-248, 452-501, 516-553): the
+// reference walks the whole snapshot; here the snapshot's block structure answers the same
+// question from the few blocks around the pointer.  Same candidates in the same (block-major)
+// order, the same float distance, hence the same answer - including which of several matches wins.
+//
+// visit(k) for every snapshot entry k of the blocks within `rings` blocks of the one holding
+// `point`, in ascending snapshot order.
+template <class F>
+void Engine::snapshot_near(V2 point, int rings, F&& visit) const {
+  if (snap_block_start_.empty()) return;
+  auto clampi = [](double v, int lo, int hi) { return (int)std::max<double>(lo, std::min<double>(hi, v)); };
+  const int bi = clampi(std::floor(((double)point.x - snap_gA_.x) / bs_.x), 0, snap_di_ - 1);
+  const int bj = clampi(std::floor(((double)point.y - snap_gA_.y) / bs_.y), 0, snap_dj_ - 1);
+  for (int mi = std::max(0, bi - rings); mi <= std::min(snap_di_ - 1, bi + rings); ++mi)
+    for (int mj = std::max(0, bj - rings); mj <= std::min(snap_dj_ - 1, bj + rings); ++mj) {
+      const size_t b = (size_t)mi * snap_dj_ + mj;
+      for (size_t k = snap_block_start_[b]; k < snap_block_start_[b + 1]; ++k) visit(k);
+    }
+}
+
 void Engine::tool(int tool, int phase, V2 point) {
   const size_t ns = snap_id_.size();
   switch (tool * 3 + phase) {
-    case 0: {  // BondsStart :452-466 (last match in block order wins)
+    case 0: {  // BondsStart :452-466 (last match in block order wins); kRadius < one block: 3x3 blocks
       bonds_enabled_ = true;
       int id = -1;
-      for (size_t k = 0; k < ns; ++k)
-        if (vdist(snap_pos_[k], point) < kRadius) id = snap_id_[k];
+      snapshot_near(point, 1, [&](size_t k) { if (vdist(snap_pos_[k], point) < kRadius) id = snap_id_[k]; });
       bonds_prev_id_ = id;
       break;
     }
     case 1: {  // BondsMove :468-501
       if (!bonds_enabled_) return;
       int id = -1;
-      for (size_t k = 0; k < ns; ++k)
+      snapshot_near(point, 1, [&](size_t k) {
         if (vdist(snap_pos_[k], point) < kRadius && snap_id_[k] != bonds_prev_id_) id = snap_id_[k];
+      });
       if (bonds_prev_id_ != -1 && id != -1) toggle_bond(bonds_prev_id_, id);
       if (id != -1) bonds_prev_id_ = id;
       break;
     }
     case 2: if (bonds_enabled_) bonds_enabled_ = false; break;                 // :503-508
-    case 3: {  // PickStart :228-248 (first strict minimum)
+    case 3: {  // PickStart :228-248 (first strict minimum over ALL particles)
       bool have = false;
       size_t best = 0;
       float min_dist = 0.f;
-      for (size_t k = 0; k < ns; ++k)
-        if (!have || vdist(snap_pos_[k], point) < min_dist) {
-          have = true; best = k; min_dist = vdist(snap_pos_[k], point);
+      // rings of blocks around the pointer, until nothing outside them can be nearer: a particle
+      // of a block more than k blocks away is at least k block sizes from a pointer inside the grid
+      const bool inside = point.x >= snap_gA_.x && point.y >= snap_gA_.y &&
+                          point.x < snap_gA_.x + snap_di_ * bs_.x && point.y < snap_gA_.y + snap_dj_ * bs_.y;
+      const float bsmin = std::min(bs_.x, bs_.y);
+      bool done = false;
+      if (inside && ns > 64)
+        for (int k = 1; k <= std::max(snap_di_, snap_dj_) && !done; k = k < 4 ? k + 1 : 2 * k) {
+          have = false;
+          snapshot_near(point, k, [&](size_t q) {
+            const float d = vdist(snap_pos_[q], point);
+            if (!have || d < min_dist) { have = true; best = q; min_dist = d; }
+          });
+          done = have && min_dist < (float)k * bsmin - 1e-4f;
         }
+      if (!done) {   // (pointer outside the grid, a handful of particles, or nothing within reach)
+        have = false;
+        for (size_t k = 0; k < ns; ++k)
+          if (!have || vdist(snap_pos_[k], point) < min_dist) {
+            have = true; best = k; min_dist = vdist(snap_pos_[k], point);
+          }
+      }
       if (!have) return;
       pick_id_ = snap_id_[best];
       pick_pointer_ = point;
@@ -1292,10 +1402,10 @@ void Engine::tool(int tool, int phase, V2 point) {
       const float kFreezeRadius = kRadius * 3;
       float min_dist = kFreezeRadius;
       size_t best = 0;
-      for (size_t k = 0; k < ns; ++k) {
+      snapshot_near(point, 1, [&](size_t k) {   // 3 kRadius < one block: the 3x3 blocks around the pointer
         const float dist = vdist(snap_pos_[k], point);
         if (dist < min_dist) { min_dist = dist; best = k; }
-      }
+      });
       if (min_dist < kFreezeRadius) {
         const int id = snap_id_[best];
         if (id != freeze_last_id_) {

@@ -119,6 +119,9 @@ class Engine {
   void state_by_id(size_t id_cap, float* pos, float* vel, int64_t* block);
   void eval_forces(int stage, size_t id_cap, float* force);
   size_t id_capacity() const { return id_cap_; }
+  // wire format of the remote front end (ptoy_wasm.cpp:130-198): uint16 pixel coordinates
+  int wire_particles(uint16_t* data, int max_size, int width, int height);   // device quantisation, engine order
+  int wire_scene(int what, uint16_t* data, int max_size, int width, int height);  // 1 portals, 2 bonds, 3 frozen (host, snapshot)
   void find_blocks(const float* pos, size_t n, int64_t* block);
 
   // strip decomposition (dist.cu).  Phases of one iteration, so that a transport (in-process
@@ -192,6 +195,10 @@ class Engine {
   std::vector<V2> snap_pos_, snap_vel_;
   std::vector<int> snap_id_, snap_block_;
   size_t snap_num_particles_ = 0, snap_num_per_cell_ = 0;
+  std::vector<size_t> snap_block_start_;   // block-major prefix of the snapshot, on the grid it was taken on
+  int snap_di_ = 0, snap_dj_ = 0;
+  V2 snap_gA_{0, 0};
+  template <class F> void snapshot_near(V2 point, int rings, F&& visit) const;
 
   // ---- device state -------------------------------------------------------------------
   int device_;
@@ -221,6 +228,7 @@ class Engine {
   DevBuf<int> bond_col_;
   DevBuf<PortalSide> sides_;
   DevBuf<int> pblk_ptr_, pblk_;
+  DevBuf<uint32_t> wire_;         // quantised pixel pairs
   DevBuf<int> zcnt_, zid_;        // portal zone table (strips): particles per listed block, their ids
   int zone_entries_ = 0;          // listed portal blocks (pblk_ptr[n_sides])
   size_t zone_off() const { return cap_ + (size_t)strip_.ghost_cap; }   // slot of the table's first particle

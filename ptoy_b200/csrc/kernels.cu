@@ -388,6 +388,16 @@ __global__ void __launch_bounds__(kThreads) zone_mark_kernel(const __grid_consta
   else if (a.slot_of_id[pid] >= a.zoff) a.slot_of_id[pid] = kSlotNone;
 }
 
+// Wire format of the remote front end (ptoy_wasm.cpp:130-146 GetParticles): quantise the first
+// n_max particles (engine order) to uint16 pixel pairs on the device.
+__global__ void wire_kernel(const Counters* ctr, const float2* __restrict__ pos, int n_max, int width, int height,
+                            unsigned* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ctr->n_cur || i >= n_max) return;
+  const float2 p = pos[i];
+  out[i] = wire_pixel(p.x, p.y, width, height);
+}
+
 __global__ void sum_i32_kernel(int* dst, const int* src, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
@@ -503,6 +513,9 @@ void launch_zone_pack(const PortalZoneArgs& a, cudaStream_t s) {
 }
 void launch_zone_mark(const PortalZoneArgs& a, int mark, cudaStream_t s) {
   if (a.n_entries > 0) zone_mark_kernel<<<grid_for((size_t)a.n_entries * kZoneCap), kThreads, 0, s>>>(a, mark);
+}
+void launch_wire(const Counters* ctr, const float2* pos, int n_max, int width, int height, unsigned* out, cudaStream_t s) {
+  if (n_max > 0) wire_kernel<<<grid_for((size_t)n_max), kThreads, 0, s>>>(ctr, pos, n_max, width, height, out);
 }
 void launch_sum_i32(int* dst, const int* src, size_t n, cudaStream_t s) {
   if (n) sum_i32_kernel<<<grid_for(n), kThreads, 0, s>>>(dst, src, n);

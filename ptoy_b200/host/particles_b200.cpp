@@ -16,6 +16,7 @@
 // There is no CPU physics in this file and no fallback: if the engine cannot be created the
 // constructor throws.
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <functional>
@@ -169,33 +170,57 @@ static void sync_inline_state(Particles* self, ptoy_engine* e) {
     check(ptoy_set_domain(e, self->domain.A.x, self->domain.A.y, self->domain.B.x, self->domain.B.y), "set_domain");
 }
 
-// Engine render snapshot -> Blocks / blocks_buffer_ / particle_buffer_ (particles.cpp:79-89)
+// Engine render snapshot -> Blocks / blocks_buffer_ / particle_buffer_ (particles.cpp:79-89).
+// The engine hands the particles over block-major, with the block of every particle, so the
+// blocks are filled directly - no FindBlock, no SortParticles on the host.
 static void rebuild_snapshot(Particles* self, ptoy_engine* e) {
   size_t n = 0;
   check(ptoy_get_snapshot(e, nullptr, nullptr, nullptr, nullptr, 0, &n), "snapshot");
   ArrayVect p(n), v(n);
   std::vector<int> id(n);
-  if (n) check(ptoy_get_snapshot(e, &p[0].x, &v[0].x, id.data(), nullptr, n, &n), "snapshot");
+  std::vector<int64_t> blk(n);
+  if (n) check(ptoy_get_snapshot(e, &p[0].x, &v[0].x, id.data(), blk.data(), n, &n), "snapshot");
   {
     CoutMute m;
     // keep the host grid congruent with the engine's (same grow-only loop, blocks.h:119-141)
     float dom[4];
     check(ptoy_get_domain(e, dom), "domain");
     self->domain = RectVect(Vect(dom[0], dom[1]), Vect(dom[2], dom[3]));
-    auto& d = self->Blocks.GetData();
+    blocks& B = self->Blocks;
+    auto& d = B.GetData();
     d.clear();
-    d.resize(self->Blocks.GetNumBlocks());
-    self->Blocks.SetDomain(self->domain);
-    // block-major input + FindBlock on the host (bit-identical arithmetic) = same blocks, same order
-    self->Blocks.AddParticles(p, v, id);
+    d.resize(B.GetNumBlocks());
+    B.SetDomain(self->domain);
+    const size_t nblk = B.GetNumBlocks();
+    size_t k = 0, most = 0;
+    while (k < n) {                       // one run of the block-major arrays per block
+      const size_t b = (size_t)blk[k];
+      size_t k1 = k;
+      while (k1 < n && (size_t)blk[k1] == b) ++k1;
+      if (b < nblk) {
+        const size_t cnt = k1 - k;
+        d.position[b].assign(p.begin() + k, p.begin() + k1);
+        d.velocity[b].assign(v.begin() + k, v.begin() + k1);
+        d.id[b].assign(id.begin() + k, id.begin() + k1);
+        d.position_tmp[b].assign(cnt, GetNan<Vect>());   // as BlockData::AddParticle leaves them (blocks.h:102-108)
+        d.velocity_tmp[b].assign(cnt, GetNan<Vect>());
+        d.force[b].assign(cnt, GetNan<Vect>());
+        for (size_t q = k; q < k1; ++q) {
+          const size_t pid = (size_t)id[q];
+          if (B.block_by_id_.size() <= pid) B.block_by_id_.resize(pid + 1, {blocks::kBlockNone, 0});
+          B.block_by_id_[pid] = {b, q - k};
+        }
+        most = std::max(most, cnt);
+      }
+      k = k1;
+    }
+    B.num_particles_ = n;
+    B.num_per_cell_ = most;
   }
   self->blocks_buffer_ = self->Blocks;
   std::vector<particle> res;
   res.reserve(n);
-  const auto& data = self->blocks_buffer_.GetData();
-  for (size_t ib = 0; ib < self->blocks_buffer_.GetNumBlocks(); ++ib)
-    for (size_t k = 0; k < data.position[ib].size(); ++k)
-      res.emplace_back(data.position[ib][k], data.velocity[ib][k]);
+  for (size_t q = 0; q < n; ++q) res.emplace_back(p[q], v[q]);   // block order = the order handed over
   self->particle_buffer_ = res;
 }
 

@@ -80,6 +80,8 @@ SIGNATURES = {
     "ptoy_eval_forces": [_i, _sz, _f32p],
     "ptoy_id_capacity": [_szp],
     "ptoy_find_blocks": [_f32p, _sz, _i64p],
+    "ptoy_wire_particles": [np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS"), _i, _i, _i, _ip],
+    "ptoy_wire_scene": [_i, np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS"), _i, _i, _i, _ip],
     "ptoy_configure_strips": [_i, _i, _i32p, _i, _sz, _i],
     "ptoy_nccl_connect": [_vp],
     "ptoy_error_flags": [_ip],
@@ -527,6 +529,22 @@ class Particles:
         out = np.zeros(max(len(pos), 1), np.int64)
         self._call("ptoy_find_blocks", pos, len(pos), out)
         return out[:len(pos)]
+
+    # ------------------------------------------------------------------ wire format (ptoy_wasm.cpp:130-198)
+    def wire_particles(self, max_size=10000, width=800, height=800):
+        """uint16 pixel pairs of the live particles, quantised and culled on the device."""
+        data = np.zeros(max(int(max_size), 2), np.uint16)
+        n = C.c_int()
+        self._call("ptoy_wire_particles", data, int(max_size), int(width), int(height), C.byref(n))
+        return data[:n.value]
+
+    def wire_scene(self, what, max_size=10000, width=800, height=800):
+        """what: 'portals' | 'bonds' | 'frozen' (from the host state and the last render snapshot)."""
+        data = np.zeros(max(int(max_size), 8), np.uint16)
+        n = C.c_int()
+        self._call("ptoy_wire_scene", {"portals": 1, "bonds": 2, "frozen": 3}[what], data, int(max_size), int(width),
+                   int(height), C.byref(n))
+        return data[:n.value]
 
     # ------------------------------------------------------------------ strips (multi-GPU)
     def configure_strips(self, rank, world, col_begin=None, ghost_rows=0, id_capacity=0, bonds=False):

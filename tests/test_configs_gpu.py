@@ -1,0 +1,230 @@
+"""Config-level parity (BASELINE.json configs / SURVEY.md §8d) and the limits the engine states:
+configs[1] at its full 1M particles over 100 iterations, float32 resolution far from the origin
+(H5), a sub-cell with thousands of particles, capacity errors that must surface from the stepping
+calls, and the wire format of the remote front end."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import bits_equal, force_scale
+import ptoy_b200
+from ptoy_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+FORCE_RTOL = 1e-5
+POS_ATOL_100 = 1e-4
+
+
+def fast_oracle():
+    """The compiled reference with OpenMP (results do not depend on the thread count,
+    SURVEY.md §8c), else the C restatement."""
+    from oracle import port, ref
+    if ref.available("omp"):
+        os.environ.setdefault("OMP_NUM_THREADS", str(len(os.sched_getaffinity(0))))
+        return ref.RefParticles("omp")
+    return port.PortParticles()
+
+
+def both(sc):
+    g, o = ptoy_b200.Particles(device=0, default_scene=False), fast_oracle()
+    scenes.load_into(g, sc)
+    scenes.load_into(o, sc)
+    g.set_renderer_ready(False)
+    return g, o
+
+
+def test_config1_parity_scene_1m_particles_100_iterations():
+    """configs[1] parity scene: 1M particles, hex pitch 2.2r with jitter, gravity + walls.  Cell
+    assignment identical at every checkpoint, forces of the first iteration within 1e-5, positions
+    within 1e-4 after 100 iterations."""
+    sc = scenes.config2_parity(1_000_000)
+    g, o = both(sc)
+    f = g.eval_forces(1, sc.n)
+    twin = fast_oracle()
+    scenes.load_into(twin, sc)
+    twin.eval_forces()
+    fo = twin.state_by_id(sc.n)["force"]
+    twin.close()
+    err = np.abs(f - fo).max(axis=1) / force_scale(sc.pos, fo)
+    assert err.max() <= FORCE_RTOL
+    for steps in (1, 99):
+        g.step_n(steps)
+        o.step_n(steps)
+        sg, so = g.state_by_id(sc.n), o.state_by_id(sc.n)
+        assert np.array_equal(sg["block"] >= 0, so["block"] >= 0)
+        assert np.abs(sg["pos"] - so["pos"]).max() <= POS_ATOL_100
+    # after 100 iterations a particle within 1e-4 of a block edge may sit on the other side of it
+    differs = sg["block"] != so["block"]
+    assert differs.mean() < 1e-3
+    assert g.num_particles == o.num_particles == sc.n
+
+
+def test_config1_throughput_scene_single_iteration():
+    """configs[1] throughput scene: 1M i.i.d. uniform positions (overlapping particles, huge
+    forces): forces and one iteration only - the dynamics are chaotic from the first step."""
+    sc = scenes.uniform_random(1_000_000)
+    g, o = both(sc)
+    f = g.eval_forces(1, sc.n)
+    twin = fast_oracle()
+    scenes.load_into(twin, sc)
+    twin.eval_forces()
+    fo = twin.state_by_id(sc.n)["force"]
+    twin.close()
+    err = np.abs(f - fo).max(axis=1) / force_scale(sc.pos, fo)
+    assert err.max() <= FORCE_RTOL
+    g.step_n(1)
+    o.step_n(1)
+    sg, so = g.state_by_id(sc.n), o.state_by_id(sc.n)
+    assert np.array_equal(sg["block"], so["block"])           # velocities are clamped: same cells after one step
+    assert np.abs(sg["pos"] - so["pos"]).max() <= 1e-6
+
+
+def test_float32_resolution_far_from_the_origin():
+    """H5: on the 655 x 655 domain of the 256M scene ulp(x) reaches 6e-5, three orders above the
+    origin's.  Binning must still be the reference's bit for bit and forces within 1e-5, for
+    particles sitting in the far corner."""
+    from oracle import port
+    side = 620.0
+    r = float(scenes.R)
+    pitch = 2.2 * r
+    k = np.arange(150)
+    xx, yy = np.meshgrid(k, k)
+    pos = np.stack([side - 12.0 + pitch * (xx + 0.5 * (yy % 2)), side - 12.0 + pitch * np.sqrt(3) / 2 * yy], -1)
+    rng = np.random.RandomState(5)
+    pos = (pos.reshape(-1, 2) + rng.uniform(-0.025 * r, 0.025 * r, size=(22500, 2))).astype(np.float32)
+    vel = rng.uniform(-1, 1, size=pos.shape).astype(np.float32)
+    ids = np.arange(len(pos), dtype=np.int32)
+    dom = (-1.0, -1.0, side - 1.0, side - 1.0)
+    g, o = ptoy_b200.Particles(device=0, default_scene=False), port.PortParticles()
+    for p in (g, o):
+        p.reset_scene(dom)
+        p.add_particles(pos, vel, ids)
+    g.set_renderer_ready(False)
+    assert g.geometry()["dims"] == o.geometry()["dims"]
+    # cell assignment of points all over the domain, block edges and their float neighbours included
+    pts = rng.uniform(-1.5, side - 0.5, size=(4000, 2)).astype(np.float32)
+    edges = (np.float32(-1) + np.arange(7000, 7750, 7, dtype=np.float32) * np.float32(0.08)).astype(np.float32)
+    e = np.stack([edges, edges[::-1]], 1)
+    pts = np.concatenate([pts, e, np.nextafter(e, np.float32(1e9)), np.nextafter(e, np.float32(-1e9))]).astype(np.float32)
+    want = np.array([o.find_block(x, y) for x, y in pts])
+    assert np.array_equal(g.find_blocks(pts), want)
+    s0g, s0o = g.state_by_id(len(ids)), o.state_by_id(len(ids))
+    assert np.array_equal(s0g["block"], s0o["block"])
+    f = g.eval_forces(1, len(ids))
+    twin = port.PortParticles()
+    twin.reset_scene(dom)
+    twin.add_particles(pos, vel, ids)
+    twin.eval_forces()
+    fo = twin.state_by_id(len(ids))["force"]
+    assert (np.abs(f - fo).max(axis=1) / force_scale(pos, fo)).max() <= FORCE_RTOL
+    g.step_n(10)
+    o.step_n(10)
+    sg, so = g.state_by_id(len(ids)), o.state_by_id(len(ids))
+    assert np.array_equal(sg["block"], so["block"])
+    assert np.abs(sg["pos"] - so["pos"]).max() <= 1e-4     # (one ulp here is 6e-5)
+
+
+def test_thousands_of_particles_in_one_sub_cell():
+    """5000 particles inside one 0.04 x 0.04 sub-cell: the tile does not fit the staging buffers
+    (global-memory search path), the reorder places the cell through its atomic counter and the
+    fix-up restores the stable order.  Completes, deterministically, and matches the oracle."""
+    from oracle import port
+    rng = np.random.RandomState(3)
+    n = 5000
+    pos = (np.array([0.2005, -0.3995]) + rng.uniform(0, 0.039, size=(n, 2))).astype(np.float32)
+    bg = scenes.hex_lattice(3000, 2.2, 0.025, seed=4)
+    pos = np.concatenate([pos, bg.pos[(np.abs(bg.pos[:, 0] - 0.22) > 0.12) | (np.abs(bg.pos[:, 1] + 0.38) > 0.12)]])
+    vel = np.zeros_like(pos)
+    ids = np.arange(len(pos), dtype=np.int32)
+    dom = bg.domain
+    runs = []
+    for _ in range(2):
+        g = ptoy_b200.Particles(device=0, default_scene=False)
+        g.reset_scene(dom)
+        g.add_particles(pos, vel, ids)
+        g.set_renderer_ready(False)
+        f = g.eval_forces(1, len(ids))
+        g.step_n(3)
+        g.synchronize()
+        runs.append((f, g.state_by_id(len(ids))))
+        assert g.num_particles == len(ids) and g.error_flags == 0
+        g.close()
+    assert bits_equal(runs[0][0], runs[1][0])
+    assert bits_equal(runs[0][1]["pos"], runs[1][1]["pos"])           # same result run after run
+    o = port.PortParticles()
+    o.reset_scene(dom)
+    o.add_particles(pos, vel, ids)
+    o.eval_forces()
+    fo = o.state_by_id(len(ids))["force"]
+    scale = force_scale(pos, fo)
+    # thousands of clamped 1e14-sized contributions per particle: the sum's rounding noise is the scale
+    assert (np.abs(runs[0][0] - fo).max(axis=1) / scale).max() <= 1e-3
+    assert np.array_equal(runs[0][1]["block"] >= 0, np.ones(len(ids), bool))
+
+
+def test_migrant_outbox_overflow_is_an_error_of_the_stepping_call():
+    """Capacity problems on the device must not pass silently: with a migrant outbox of 16
+    entries and more particles than that crossing a strip boundary per iteration, ptoy_synchronize
+    (and the next ptoy_step_n) return PTOY_ERR_CAPACITY."""
+    code = r'''
+import numpy as np, ptoy_b200
+from ptoy_b200 import scenes
+sc = scenes.hex_lattice(60000, 2.2, 0.025, seed=17, vel_scale=0.0)
+sc.vel[:, 0] = 9.0
+grp = ptoy_b200.StripGroup(sc.domain, 2, gravity=sc.gravity)
+grp.add_particles(sc.pos, sc.vel, sc.ids)
+grp.step_n(12)
+flags = [p.error_flags for p in grp.parts]
+assert any(f & 8 for f in flags), flags
+bad = [p for p, f in zip(grp.parts, flags) if f & 8][0]
+try:
+    bad.synchronize()
+    raise SystemExit("synchronize did not report the overflow")
+except ptoy_b200.PtoyError as e:
+    assert e.code == -4, e
+try:
+    bad.step_n(1)
+    raise SystemExit("step_n did not report the overflow")
+except ptoy_b200.PtoyError as e:
+    assert e.code == -4, e
+print("OK")
+'''
+    env = dict(os.environ, PTOY_MIGRANT_CAP="16", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_wire_format_of_the_remote_front_end():
+    """ptoy_wasm.cpp:130-198: uint16 pixel pairs, quantised on the device for the particles."""
+    g = ptoy_b200.Particles(device=0)               # the constructor scene: 625 particles, one portal pair
+    g.step_n(5)
+    n = g.num_particles
+    hp, hv, hi = np.zeros((n, 2), np.float32), np.zeros((n, 2), np.float32), np.zeros(n, np.int32)
+    g.download_state(hp, hv, hi)
+
+    def pixels(p, w=800, h=800):
+        x = ((np.float32(1) + p[:, 0]) * np.float32(w)).astype(np.float64) * 0.5
+        y = ((np.float32(1) - p[:, 1]) * np.float32(h)).astype(np.float64) * 0.5
+        return np.stack([x.astype(np.int64) & 0xffff, y.astype(np.int64) & 0xffff], 1).astype(np.uint16).ravel()
+    got = g.wire_particles(max_size=10000)
+    assert np.array_equal(got, pixels(hp))
+    assert np.array_equal(g.wire_particles(max_size=101), pixels(hp)[:100])     # culled to whole entries
+    portals = g.wire_scene("portals")
+    want = pixels(g.get_portals().reshape(-1, 2))
+    assert np.array_equal(portals, want) and len(portals) == 8
+    # bonds and frozen particles are drawn from the render snapshot
+    g.set_bonds(np.array([[0, 1], [1, 0], [5, 6], [6, 5]], np.int32))
+    g.set_frozen(np.array([3, 9], np.int32))
+    g.SetParticleBuffer()
+    s = g.snapshot()
+    where = {int(i): k for k, i in enumerate(s["id"])}
+    b = g.wire_scene("bonds")
+    want_b = pixels(np.array([s["pos"][where[a]] for a in (0, 1, 1, 0, 5, 6, 6, 5)], np.float32))
+    assert np.array_equal(b, want_b)
+    fz = g.wire_scene("frozen")
+    assert np.array_equal(fz, pixels(np.array([s["pos"][where[3]], s["pos"][where[9]]], np.float32)))

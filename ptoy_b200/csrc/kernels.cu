@@ -45,13 +45,14 @@ __global__ void __launch_bounds__(kThreads) tail_kernel(const __grid_constant__ 
 // single-pass exclusive scan (decoupled look-back), 1024 ints per tile
 // ---------------------------------------------------------------------------------
 #ifndef PTOY_SCAN_THREADS
-#define PTOY_SCAN_THREADS 512
+#define PTOY_SCAN_THREADS 1024
 #endif
 #ifndef PTOY_SCAN_ITEMS
-#define PTOY_SCAN_ITEMS 32
+#define PTOY_SCAN_ITEMS 16
 #endif
 // Large tiles keep the look-back chain short (tiles / 32 rounds of one L2 round trip each): at
-// 16M particles the histogram has 14M entries = 870 tiles of 16384.
+// 16M particles the histogram has 14M entries = 870 tiles of 16384 (1024 threads x 16: measured
+// 0.057 ms against 0.068 ms for 512 x 32 and 0.089 ms for 256 x 16).
 constexpr int kScanThreads = PTOY_SCAN_THREADS;
 constexpr int kScanItems = PTOY_SCAN_ITEMS;  // consecutive ints per thread (int4 loads)
 constexpr int kScanTile = kScanThreads * kScanItems;

@@ -81,7 +81,7 @@ def test_config1_throughput_scene_single_iteration():
     o.step_n(1)
     sg, so = g.state_by_id(sc.n), o.state_by_id(sc.n)
     assert np.array_equal(sg["block"], so["block"])           # velocities are clamped: same cells after one step
-    assert np.abs(sg["pos"] - so["pos"]).max() <= 1e-6
+    assert np.abs(sg["pos"] - so["pos"]).max() <= 1e-5        # (coordinates reach 47: one ulp is 3.8e-6)
 
 
 def test_float32_resolution_far_from_the_origin():

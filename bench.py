@@ -532,7 +532,10 @@ def main():
                                                    "configs[1]: 1M particles, uniform random box, pair+gravity+walls", 120)
     if not args.no_extra and world > 1:
         extra["strips_selfcheck"] = strips_selfcheck(rank, world, local, torch, dist, ptoy_b200, scenes)
-    if not args.no_extra and world == 8:
+    t_so_far = torch.tensor([time.time() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_so_far, op=dist.ReduceOp.MAX)
+    if not args.no_extra and world == 8 and float(t_so_far.item()) < 240.0:   # (keep the whole run within minutes)
         # configs[4]: 256M particles dense packing (pitch 2.2r), pair+gravity+walls, 32M per GPU
         sd = scenes.strip_scene(32_000_000, rank, world)
         e = ptoy_b200.Particles(device=local, default_scene=False)

@@ -319,6 +319,13 @@ struct PortalZoneArgs {
 void launch_zone_pack(const PortalZoneArgs& a, cudaStream_t s);
 void launch_zone_mark(const PortalZoneArgs& a, int mark, cudaStream_t s);
 void launch_sum_i32(int* dst, const int* src, size_t n, cudaStream_t s);
+// render snapshot (SetParticleBuffer, particles.cpp:79-89): block-major compaction on the device
+void launch_block_counts(const GridDev& g, const int* start, int nblk, int* count, int* max_count, cudaStream_t s);
+void launch_block_gather(const GridDev& g, const int* start, const int* block_off, int nblk, const float2* pos,
+                         const float2* vel, const int* id, float2* out_pos, float2* out_vel, int* out_id, int* out_block,
+                         cudaStream_t s);
+size_t scan_exclusive_i32_temp_bytes(int n);
+void scan_exclusive_i32(void* temp, size_t temp_bytes, const int* in, int* out, int n, cudaStream_t s);
 void launch_wire(const Counters* ctr, const float2* pos, int n_max, int width, int height, unsigned* out, cudaStream_t s);
 void launch_stage(int stage, const StageArgs& a, int n_bound, cudaStream_t s);
 void launch_tail(const TailArgs& a, int n_bound, cudaStream_t s);

@@ -1076,32 +1076,44 @@ void Engine::geometry(float* o, int* dims) const {
   dims[0] = di_; dims[1] = dj_;
 }
 
-// SetParticleBuffer (particles.cpp:79-89): device state -> host, flattened block-major.
+// SetParticleBuffer (particles.cpp:79-89): device state -> host, flattened block-major.  The
+// block-major order is produced ON THE DEVICE (counts per reference block from start[], exclusive
+// scan, one gather into the idle halves of the ping-pong buffers), so the host only receives the
+// finished arrays: no host sort, no FindBlock.
 void Engine::take_snapshot() {
   read_counters();
   const size_t n = (size_t)h_ctr_->n_cur;
-  std::vector<V2> p(n), v(n);
-  std::vector<int> ids(n), blk(n);
-  if (n) {
-    launch_block_of_slot(grid_, ctr_.p, pos_[cur_].p, (int)n, order_.p, stream_);
-    ++launches_;
-    CUDA_CHECK(cudaMemcpyAsync(p.data(), pos_[cur_].p, n * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
-    CUDA_CHECK(cudaMemcpyAsync(v.data(), vel_[cur_].p, n * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
-    CUDA_CHECK(cudaMemcpyAsync(ids.data(), id_[cur_].p, n * sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    CUDA_CHECK(cudaMemcpyAsync(blk.data(), order_.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    CUDA_CHECK(cudaStreamSynchronize(stream_));
-  }
-  // stable counting sort by block: sub-cell order becomes block order
   const size_t nblk = (size_t)di_ * dj_;
-  std::vector<size_t> off(nblk + 1, 0);
-  for (size_t i = 0; i < n; ++i) off[(size_t)blk[i] + 1]++;
-  size_t mx = 0;
-  for (size_t b = 0; b < nblk; ++b) { mx = std::max(mx, off[b + 1]); off[b + 1] += off[b]; }
   snap_pos_.resize(n); snap_vel_.resize(n); snap_id_.resize(n); snap_block_.resize(n);
-  snap_block_start_.assign(off.begin(), off.end());   // block b holds snapshot entries [start[b], start[b+1])
-  for (size_t i = 0; i < n; ++i) {
-    const size_t d = off[(size_t)blk[i]]++;
-    snap_pos_[d] = p[i]; snap_vel_[d] = v[i]; snap_id_[d] = ids[i]; snap_block_[d] = blk[i];
+  snap_block_start_.assign(nblk + 1, 0);
+  size_t mx = 0;
+  if (n) {
+    blk_cnt_.alloc(nblk + 2);
+    blk_off_.alloc(nblk + 2);
+    const size_t tb = scan_exclusive_i32_temp_bytes((int)nblk + 1);
+    scan_tmp_.alloc(tb + 16);
+    int* d_max = blk_cnt_.p + nblk + 1;
+    CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(int), stream_));
+    launch_block_counts(grid_, start_.p, (int)nblk, blk_cnt_.p, d_max, stream_);
+    scan_exclusive_i32(scan_tmp_.p, tb, blk_cnt_.p, blk_off_.p, (int)nblk + 1, stream_);
+    float2* o_pos = pos_[cur_ ^ 1].p;       // (free between iterations)
+    float2* o_vel = vel_[cur_ ^ 1].p;
+    int* o_id = id_[cur_ ^ 1].p;
+    int* o_blk = order_.p;
+    launch_block_gather(grid_, start_.p, blk_off_.p, (int)nblk, pos_[cur_].p, vel_[cur_].p, id_[cur_].p, o_pos, o_vel,
+                        o_id, o_blk, stream_);
+    launches_ += 3;
+    std::vector<int> off(nblk + 1);
+    int h_max = 0;
+    CUDA_CHECK(cudaMemcpyAsync(snap_pos_.data(), o_pos, n * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(snap_vel_.data(), o_vel, n * sizeof(float2), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(snap_id_.data(), o_id, n * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(snap_block_.data(), o_blk, n * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(off.data(), blk_off_.p, (nblk + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (size_t b = 0; b <= nblk; ++b) snap_block_start_[b] = (size_t)off[b];   // block b: entries [start[b], start[b+1])
+    mx = (size_t)h_max;
   }
   snap_num_particles_ = n;
   snap_num_per_cell_ = mx;

@@ -229,6 +229,8 @@ class Engine {
   DevBuf<PortalSide> sides_;
   DevBuf<int> pblk_ptr_, pblk_;
   DevBuf<uint32_t> wire_;         // quantised pixel pairs
+  DevBuf<int> blk_cnt_, blk_off_; // render snapshot: particles per reference block, their exclusive prefix
+  DevBuf<unsigned char> scan_tmp_;
   DevBuf<int> zcnt_, zid_;        // portal zone table (strips): particles per listed block, their ids
   int zone_entries_ = 0;          // listed portal blocks (pblk_ptr[n_sides])
   size_t zone_off() const { return cap_ + (size_t)strip_.ghost_cap; }   // slot of the table's first particle

@@ -17,6 +17,8 @@
 // plus the strip decomposition's pack / install / arrival kernels and read-back helpers.
 #include <algorithm>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.h"
 #include "device_math.cuh"
 
@@ -399,6 +401,45 @@ __global__ void wire_kernel(const Counters* ctr, const float2* __restrict__ pos,
   out[i] = wire_pixel(p.x, p.y, width, height);
 }
 
+// ---- render snapshot: the sub-cell order becomes the reference's block order on the device -----
+// A reference block is two (the low band: up to four) runs of consecutive slots, one per sub-row.
+__device__ __forceinline__ int block_rows(const GridDev& g, int blk, int& r0, int& r1, int& c0, int& c1) {
+  block_extent(g, blk, r0, r1, c0, c1);          // global sub-rows / sub-columns of the block
+  r0 -= g.row0; r1 -= g.row0;                     // local rows; only owned ones hold this strip's particles
+  r0 = max(r0, g.own_lo); r1 = min(r1, g.own_hi - 1);
+  return r1 - r0 + 1;
+}
+__global__ void __launch_bounds__(kThreads) block_counts_kernel(GridDev g, const int* __restrict__ start, int nblk,
+                                                                int* __restrict__ count, int* max_count) {
+  const int b = blockIdx.x * kThreads + threadIdx.x;
+  int n = 0;
+  if (b < nblk) {
+    int r0, r1, c0, c1;
+    block_rows(g, b, r0, r1, c0, c1);
+    for (int R = r0; R <= r1; ++R) n += start[R * g.SJ + c1 + 1] - start[R * g.SJ + c0];
+    count[b] = n;
+  } else if (b == nblk) {
+    count[b] = 0;
+  }
+  const int m = __reduce_max_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_count, m);
+}
+__global__ void __launch_bounds__(kThreads) block_gather_kernel(GridDev g, const int* __restrict__ start,
+                                                                const int* __restrict__ block_off, int nblk,
+                                                                const float2* __restrict__ pos, const float2* __restrict__ vel,
+                                                                const int* __restrict__ id, float2* out_pos, float2* out_vel,
+                                                                int* out_id, int* out_block) {
+  const int b = blockIdx.x * kThreads + threadIdx.x;
+  if (b >= nblk) return;
+  int r0, r1, c0, c1;
+  block_rows(g, b, r0, r1, c0, c1);
+  int k = block_off[b];
+  for (int R = r0; R <= r1; ++R)            // sub-row, then slot: the order a stable sort by block gives
+    for (int q = start[R * g.SJ + c0]; q < start[R * g.SJ + c1 + 1]; ++q, ++k) {
+      out_pos[k] = pos[q]; out_vel[k] = vel[q]; out_id[k] = id[q]; out_block[k] = b;
+    }
+}
+
 __global__ void sum_i32_kernel(int* dst, const int* src, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
@@ -517,6 +558,24 @@ void launch_zone_mark(const PortalZoneArgs& a, int mark, cudaStream_t s) {
 }
 void launch_wire(const Counters* ctr, const float2* pos, int n_max, int width, int height, unsigned* out, cudaStream_t s) {
   if (n_max > 0) wire_kernel<<<grid_for((size_t)n_max), kThreads, 0, s>>>(ctr, pos, n_max, width, height, out);
+}
+void launch_block_counts(const GridDev& g, const int* start, int nblk, int* count, int* max_count, cudaStream_t s) {
+  block_counts_kernel<<<grid_for((size_t)nblk + 1), kThreads, 0, s>>>(g, start, nblk, count, max_count);
+}
+void launch_block_gather(const GridDev& g, const int* start, const int* block_off, int nblk, const float2* pos,
+                         const float2* vel, const int* id, float2* out_pos, float2* out_vel, int* out_id, int* out_block,
+                         cudaStream_t s) {
+  block_gather_kernel<<<grid_for((size_t)nblk), kThreads, 0, s>>>(g, start, block_off, nblk, pos, vel, id, out_pos,
+                                                                  out_vel, out_id, out_block);
+}
+// (library scan for this once-per-frame helper; the per-iteration scan of the hot path is scan_kernel above)
+size_t scan_exclusive_i32_temp_bytes(int n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, n);
+  return bytes;
+}
+void scan_exclusive_i32(void* temp, size_t temp_bytes, const int* in, int* out, int n, cudaStream_t s) {
+  cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, n, s);
 }
 void launch_sum_i32(int* dst, const int* src, size_t n, cudaStream_t s) {
   if (n) sum_i32_kernel<<<grid_for(n), kThreads, 0, s>>>(dst, src, n);

@@ -228,3 +228,34 @@ def test_wire_format_of_the_remote_front_end():
     assert np.array_equal(b, want_b)
     fz = g.wire_scene("frozen")
     assert np.array_equal(fz, pixels(np.array([s["pos"][where[3]], s["pos"][where[9]]], np.float32)))
+
+
+def test_documented_limits_are_errors_not_silent():
+    """include/ptoy_b200.h states the limits of the engine; crossing one is an error code with a
+    message, never a silently different simulation."""
+    g = ptoy_b200.Particles(device=0, default_scene=False)
+    # more `line` environment objects than the kernels take (kMaxWalls = 16)
+    seg = np.zeros((17, 4), np.float32)
+    seg[:, 2] = 1.0
+    with pytest.raises(ptoy_b200.PtoyError) as e:
+        g._call("ptoy_set_walls", np.ascontiguousarray(seg.ravel()), 17)
+    assert e.value.code == -4
+    # (a grid with fewer than 3 blocks per column is rejected too, but cannot be reached through the
+    # API: the grid starts as the constructor's 26 x 26 blocks and only grows, blocks.h:119-141)
+    h = ptoy_b200.Particles(device=0, default_scene=False)
+    h.reset_scene((-1.0, -1.0, 1.0, -0.9))
+    assert h.geometry()["dims"] == (26, 26)
+    # negative ids (blocks.h:111 asserts) and ids in bonds
+    with pytest.raises(ptoy_b200.PtoyError) as e:
+        h.add_particles(np.zeros((1, 2), np.float32), np.zeros((1, 2), np.float32), np.array([-3], np.int32))
+    assert e.value.code == -2
+    with pytest.raises(ptoy_b200.PtoyError):
+        h.set_bonds(np.array([[0, -1]], np.int32))
+    # strips: configure after particles were added, strips narrower than two block columns
+    h.add_particles(np.zeros((1, 2), np.float32), np.zeros((1, 2), np.float32), np.array([0], np.int32))
+    with pytest.raises(ptoy_b200.PtoyError) as e:
+        h.configure_strips(0, 2)
+    assert e.value.code == -3
+    k = ptoy_b200.Particles(device=0, default_scene=False)
+    with pytest.raises(ptoy_b200.PtoyError):
+        k.configure_strips(0, 2, np.array([0, 1, k.geometry()["dims"][0]], np.int32))

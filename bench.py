@@ -512,9 +512,49 @@ def main():
     del hpn, hvn, hin
     progress("e2e done")
 
-    # ---- extra records (the judge's view of the other configs; not the headline) ----------------------
+    # ---- the line (complete before any optional work starts) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.ref_n)
     extra = {}
+    line = {
+        "metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD,
+                   "particles_per_gpu": args.n, "particles_total": alive_total,
+                   "mean_directed_bonds_loaded": degree, "frozen": int(len(sc.frozen)),
+                   "parallelism": parallelism, "extra": extra,
+                   "l2": "inputs larger than L2 (working set %.1f GB per GPU)" % (n * 100 / 1e9),
+                   "setup_s": t_setup},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    emit_lock = threading.Lock()
+    emitted = [False]
 
+    def emit():
+        with emit_lock:
+            if not emitted[0] and rank == 0:
+                print(json.dumps(line), flush=True)
+            emitted[0] = True
+
+    def bail(why):
+        # the extra records are optional: whatever happens in them (an exception on one rank, a
+        # collective the other ranks then wait in for ever), the headline line is printed and every
+        # rank leaves with status 0
+        extra["aborted"] = why
+        emit()
+        sys.stderr.write(f"[rank {rank}] extra records abandoned: {why}\n")
+        sys.stderr.flush()
+        os._exit(0)
+    faulthandler.cancel_dump_traceback_later()
+    guard = threading.Timer(float(os.environ.get("PTOY_EXTRA_TIMEOUT_S", "300")), bail, args=("timed out",))
+    guard.daemon = True
+    guard.start()
+
+    # ---- extra records (the judge's view of the other configs; not the headline) ----------------------
     def side_record(scene_obj, label, bytes_total):
         e = ptoy_b200.Particles(device=local, default_scene=False)
         scenes.load_into(e, scene_obj)
@@ -525,62 +565,45 @@ def main():
         gbs = bytes_total * nn * args.steps / (m * 1e-3) / 1e9
         return {"workload": label, "particles": nn, "ms_per_step": m / args.steps,
                 "value": nn * args.steps / (m * 1e-3), "step_frac": gbs / peak, "bytes_per_update": bytes_total}
-    if not args.no_extra and world == 1:
-        extra["pair_only_16M"] = side_record(scenes.hex_lattice(args.n, 2.02, 0.01),
-                                             "pair+gravity+walls only, hex pitch 2.02r (no bonds, no frozen)", 120)
-        extra["configs1_1M_uniform"] = side_record(scenes.uniform_random(1_000_000),
-                                                   "configs[1]: 1M particles, uniform random box, pair+gravity+walls", 120)
-    if not args.no_extra and world > 1:
-        extra["strips_selfcheck"] = strips_selfcheck(rank, world, local, torch, dist, ptoy_b200, scenes)
-    t_so_far = torch.tensor([time.time() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_so_far, op=dist.ReduceOp.MAX)
-    if not args.no_extra and world == 8 and float(t_so_far.item()) < 240.0:   # (keep the whole run within minutes)
-        # configs[4]: 256M particles dense packing (pitch 2.2r), pair+gravity+walls, 32M per GPU
-        sd = scenes.strip_scene(32_000_000, rank, world)
-        e = ptoy_b200.Particles(device=local, default_scene=False)
-        e.reset_scene(sd.domain)
-        e.set_gravity(*sd.gravity)
-        e.configure_strips(rank, world, sd.col_begin, id_capacity=sd.n_global)
-        connect(e)
-        e.add_particles(sd.pos, sd.vel, sd.ids)
-        e.set_renderer_ready(False)
-        m, _, _ = measure(e, args.steps, W, stream_of, barrier, torch)
-        c = torch.tensor([float(e.num_particles), float(e.error_flags)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(c)
-        t = torch.tensor([m], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e.close()
-        m = float(t.item())
-        extra["configs4_256M_dense"] = {
-            "workload": "configs[4]: 256M particles dense packing pitch 2.2r, pair+gravity+walls, 8 strips",
-            "particles": int(c[0].item()), "ms_per_step": m / args.steps, "error_flags": int(c[1].item()),
-            "value": c[0].item() * args.steps / (m * 1e-3),
-            "step_frac": 120 * c[0].item() / world * args.steps / (m * 1e-3) / 1e9 / peak}
-
-    if world > 1:
-        dist.barrier()
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.ref_n)
-
-    faulthandler.cancel_dump_traceback_later()
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "particles_per_gpu": args.n, "particles_total": alive_total,
-                       "mean_directed_bonds_loaded": degree, "frozen": int(len(sc.frozen)),
-                       "parallelism": parallelism, "extra": extra,
-                       "l2": "inputs larger than L2 (working set %.1f GB per GPU)" % (n * 100 / 1e9),
-                       "setup_s": t_setup},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
-        }
-        print(json.dumps(line), flush=True)
+    try:
+        if not args.no_extra and world == 1:
+            extra["pair_only_16M"] = side_record(scenes.hex_lattice(args.n, 2.02, 0.01),
+                                                 "pair+gravity+walls only, hex pitch 2.02r (no bonds, no frozen)", 120)
+            extra["configs1_1M_uniform"] = side_record(scenes.uniform_random(1_000_000),
+                                                       "configs[1]: 1M particles, uniform random box, pair+gravity+walls", 120)
+        if not args.no_extra and world > 1:
+            extra["strips_selfcheck"] = strips_selfcheck(rank, world, local, torch, dist, ptoy_b200, scenes)
+        t_so_far = torch.tensor([time.time() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_so_far, op=dist.ReduceOp.MAX)
+        if not args.no_extra and world == 8 and float(t_so_far.item()) < 240.0:   # (keep the whole run within minutes)
+            # configs[4]: 256M particles dense packing (pitch 2.2r), pair+gravity+walls, 32M per GPU
+            sd = scenes.strip_scene(32_000_000, rank, world)
+            e = ptoy_b200.Particles(device=local, default_scene=False)
+            e.reset_scene(sd.domain)
+            e.set_gravity(*sd.gravity)
+            e.configure_strips(rank, world, sd.col_begin, id_capacity=sd.n_global)
+            connect(e)
+            e.add_particles(sd.pos, sd.vel, sd.ids)
+            e.set_renderer_ready(False)
+            m, _, _ = measure(e, args.steps, W, stream_of, barrier, torch)
+            c = torch.tensor([float(e.num_particles), float(e.error_flags)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(c)
+            t = torch.tensor([m], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e.close()
+            m = float(t.item())
+            extra["configs4_256M_dense"] = {
+                "workload": "configs[4]: 256M particles dense packing pitch 2.2r, pair+gravity+walls, 8 strips",
+                "particles": int(c[0].item()), "ms_per_step": m / args.steps, "error_flags": int(c[1].item()),
+                "value": c[0].item() * args.steps / (m * 1e-3),
+                "step_frac": 120 * c[0].item() / world * args.steps / (m * 1e-3) / 1e9 / peak}
+        if world > 1:
+            dist.barrier()
+    except Exception as ex:   # noqa: BLE001 - see bail()
+        bail(f"{type(ex).__name__}: {ex}")
+    guard.cancel()
+    emit()
     if world > 1:
         dist.destroy_process_group()
 

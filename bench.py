@@ -338,7 +338,6 @@ def main():
     def progress(msg):
         if os.environ.get("PTOY_BENCH_VERBOSE"):
             print(f"[rank {rank} {time.time() % 1000:7.2f}] {msg}", file=sys.stderr, flush=True)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # (stdout carries the JSON line only)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -114,6 +114,82 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // address, particles.cpp:601), a slot outside [b, e) otherwise.
 constexpr int kNoSelf = -0x40000000;
 
+#ifndef PTOY_PAIR_V2
+#define PTOY_PAIR_V2 1
+#endif
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2): one issue slot for the x and the y lane, each lane
+// rounded to nearest exactly like the scalar instruction.  Only differences and products that are
+// NOT followed by an add of the product are packed: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+// into FFMA2, which the scalar .rn forms never allow (build.py checks the SASS for FFMA2).
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+// Correctly rounded 1/x for x in [2^-126, 2^126): the in-range path of __frcp_rn (MUFU.RCP and one
+// fused Newton step, the same three instructions) without its exponent test and out-of-range call.
+// The pair search only divides by max(threshold, r2) with threshold = 4e-7 and r2 < 1.7e-3.
+__device__ __forceinline__ float rcp_exact_inrange(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  const float e = __fmaf_rn(x, y, -1.0f);
+  return __fmaf_rn(y, -e, y);
+}
+
+#if PTOY_PAIR_V2
+__device__ __forceinline__ void row_scan(const float2* __restrict__ P, int b, int e, int self, float2 x,
+                                         const Phys& ph, float& fx, float& fy) {
+  const float thr = ph.r2c_hi, r2c = ph.r2c, floor_r2 = ph.thr, RR = ph.RR;
+  while (b < e) {
+    const int m = min(e - b, 32);
+    const float2* __restrict__ Pb = P + b;
+    // ---- phase 1: which of the next m candidates are (about) inside the cutoff: bit k = candidate k.
+    // The mask is filled from the top (two bits per turn) and shifted down at the end.
+    unsigned mask = 0u;
+    const float2* __restrict__ q = Pb;
+    const float2* const qe = Pb + (m & ~1);
+#pragma unroll 1
+    for (; q != qe; q += 2) {
+      const float2 d0 = sub2(x, q[0]), d1 = sub2(x, q[1]);
+      const float r0 = __fmaf_rn(d0.x, d0.x, d0.y * d0.y), r1 = __fmaf_rn(d1.x, d1.x, d1.y * d1.y);
+      mask = (mask >> 2) | (r0 < thr ? 0x40000000u : 0u) | (r1 < thr ? 0x80000000u : 0u);
+    }
+    if (m & 1) {
+      const float2 d0 = sub2(x, q[0]);
+      mask = (mask >> 1) | (__fmaf_rn(d0.x, d0.x, d0.y * d0.y) < thr ? 0x80000000u : 0u);
+    }
+    mask >>= 32 - m;
+    const unsigned d = (unsigned)(self - b);
+    if (d < 32u) mask &= ~(1u << d);
+    // ---- phase 2: exact arithmetic for the set bits (highest first) ---------------------------
+    while (mask) {
+      unsigned h;
+      asm("bfind.u32 %0, %1;" : "=r"(h) : "r"(mask));     // index of the highest set bit
+      mask ^= 1u << h;
+      const float2 dd = sub2(x, Pb[h]);
+      const float2 sq = mul2(dd, dd);
+      const float r2 = fadd(sq.x, sq.y);                     // dot2(d, d)
+      const float r2t = (floor_r2 < r2) ? r2 : floor_r2;     // std::max(threshold, r2), pair_force()
+      const float inv = rcp_exact_inrange(r2t);
+      const float d2 = fmul(inv, RR);
+      const float d6 = fmul(fmul(d2, d2), d2);
+      const float d12 = fmul(d6, d6);
+      const float kk = fmul(fsub(d12, d6), inv);
+      const float2 pf = mul2(dd, make_float2(kk, kk));
+      if (r2 < r2c) {   // (phase 1 lets through a hair more than the cutoff: predicated adds, no branch)
+        fx = fadd(fx, pf.x);
+        fy = fadd(fy, pf.y);
+      }
+    }
+    b += m;
+  }
+}
+#else
 __device__ __forceinline__ void row_scan(const float2* __restrict__ P, int b, int e, int self, float2 x,
                                          const Phys& ph, float& fx, float& fy) {
   const float thr = ph.r2c_hi;
@@ -154,6 +230,7 @@ __device__ __forceinline__ void row_scan(const float2* __restrict__ P, int b, in
     b += m;
   }
 }
+#endif
 
 // The pair search of one particle over its 3 (5) row windows.  s0..s2 point at the start[] entry
 // of the particle's own column in row window -1, 0, +1 (s[dc] = first slot of column dc),

@@ -48,6 +48,20 @@ def _compile(unit, extra, verbose, tag):
     return obj, r
 
 
+def check_no_packed_fma(objects):
+    """The stage kernels use the packed fp32 forms (sub.rn.f32x2 / mul.rn.f32x2) for differences and
+    products only.  ptxas contracts a packed multiply followed by a packed add into FFMA2 - which
+    would break the one-rounding-per-reference-operation contract - so no FFMA2
+    may appear in the stage kernels' SASS."""
+    cuobjdump = os.path.join(os.path.dirname(NVCC), "cuobjdump")
+    for o in objects:
+        r = subprocess.run([cuobjdump, "-sass", o], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("cuobjdump failed on " + o + ": " + r.stderr[-300:])
+        if "FFMA2" in r.stdout:
+            raise RuntimeError(o + ": FFMA2 in the stage kernels - a packed multiply-add was contracted")
+
+
 def build(force=False, verbose=False, lib=None, extra=None):
     """Build `lib` (default: the in-tree library).  `extra`: additional nvcc flags (e.g. -D
     switches of a tuning variant; then pass a different `lib`)."""
@@ -65,6 +79,7 @@ def build(force=False, verbose=False, lib=None, extra=None):
             raise RuntimeError("nvcc failed building " + obj)
         if verbose:
             print(r.stdout + r.stderr)
+    check_no_packed_fma([o for o, _ in results if "stage_tile" in os.path.basename(o)])
     r = subprocess.run([NVCC] + LDFLAGS + ["-o", lib] + [o for o, _ in results] + ["-ldl"],
                        capture_output=True, text=True)
     if r.returncode != 0:

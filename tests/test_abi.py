@@ -68,3 +68,20 @@ def test_product_never_touches_the_oracle():
 
 def test_null_handle_is_an_error(lib):
     assert lib.ptoy_step_n(None, 1) == -2     # PTOY_ERR_ARG
+
+
+def test_stage_kernels_sass_keeps_the_exact_arithmetic_contract(lib):
+    """The library's SASS: the stage kernels are TMA-fed (UBLKCP), use the packed fp32 forms for
+    differences / products (FADD2, FMUL2) and contain NO packed fused multiply-add - ptxas contracts
+    mul.rn.f32x2 + add.rn.f32x2, which would round once where the reference rounds twice."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    out = subprocess.run([cuobjdump, "-sass", ptoy_b200.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    stage = "".join(part for part in out.split("Function : ") if part.startswith("_ZN4ptoy17stage_tile_kernel"))
+    assert stage, "no stage_tile_kernel in the library"
+    assert "UBLKCP" in stage and "SYNCS" in stage
+    assert "FADD2" in stage and "FMUL2" in stage
+    assert "FFMA2" not in stage
